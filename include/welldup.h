@@ -1,0 +1,174 @@
+/*
+ * welldup.h -- C ABI of libwelldup.so, the B200 (sm_100a) implementation of the
+ * well_duplicates hot path.
+ *
+ * The reference (EdinburghGenomics/well_duplicates) is pure Python and has no
+ * FFI; the seams this library sits behind are its two CLIs and its Python
+ * reader API.  Each entry point below names the reference code it replaces
+ * (file:line under the reference tree).  The ctypes binding that a maintainer
+ * of the reference would add is shown in INTEGRATION.md and shipped as
+ * well_duplicates_b200/_lib.py.
+ *
+ * Conventions
+ *  - every function returns an int status: WD_OK or a negative WD_E_* class
+ *    that tells the Python side which exception the reference would have
+ *    raised; the text is available from wd_last_error() (thread local);
+ *  - nothing throws across the boundary;
+ *  - host pointers are borrowed: pageable memory is consumed before the call
+ *    returns; memory obtained from wd_host_alloc() (pinned) is read
+ *    asynchronously and must stay unchanged until the next wd_sync() or
+ *    result-returning call (wd_count, wd_get_seqs, ...) on that context;
+ *  - all device memory belongs to the wd_ctx and is released by wd_destroy();
+ *  - output arrays are allocated by the caller;
+ *  - one wd_ctx per GPU, not thread-safe; work is asynchronous on the
+ *    context's stream until a result-returning call or wd_sync().
+ *
+ * There is no CPU fallback: wd_create() fails when no CUDA device is usable.
+ */
+#ifndef WELLDUP_H
+#define WELLDUP_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define WD_ABI_VERSION 1
+
+#if defined(__GNUC__)
+#define WD_API __attribute__((visibility("default")))
+#else
+#define WD_API
+#endif
+
+#define WD_OK 0
+#define WD_E_INDEX (-1)    /* IndexError: well index out of range (bcl_direct_reader.py:186-192) */
+#define WD_E_RUNTIME (-2)  /* RuntimeError: a target has an empty ring (prepare_cluster_indexes.py:70-76) */
+#define WD_E_ASSERT (-3)   /* AssertionError: header / size mismatch (bcl_direct_reader.py:338, :236) */
+#define WD_E_CUDA (-4)     /* CUDA runtime failure */
+#define WD_E_ARG (-5)      /* ValueError: argument outside what the library supports */
+#define WD_E_CAPACITY (-6) /* caller's output array too small; required size is reported */
+
+#define WD_MAX_LEVELS 15   /* rings per target (the reference's MAX_DISTS gives 5) */
+#define WD_MAX_SEQ_LEN 1024 /* compared symbols per well (sum of all --cycles ranges) */
+
+/* plane kinds for wd_tile_put_* */
+#define WD_PLANE_EMPTY 0
+#define WD_PLANE_BCL 1       /* 1 byte / well */
+#define WD_PLANE_CBCL 2      /* 4 bits / well, every well stored */
+#define WD_PLANE_CBCL_EXCL 3 /* 4 bits / well, pass-filter wells only */
+
+typedef struct wd_ctx wd_ctx;
+
+/* ---- context -------------------------------------------------------------- */
+WD_API int wd_abi_version(void);
+WD_API const char *wd_last_error(void);
+WD_API int wd_create(int device, wd_ctx **out);
+WD_API int wd_destroy(wd_ctx *ctx);
+/* Run on a caller-owned cudaStream_t (e.g. torch's current stream) instead of
+ * the context's own; pass NULL to return to the private stream. */
+WD_API int wd_set_stream(wd_ctx *ctx, void *cuda_stream);
+WD_API int wd_sync(wd_ctx *ctx);
+/* Pinned host memory, so that wd_tile_put_* / wd_locs_load copy by DMA without staging. */
+WD_API int wd_host_alloc(size_t bytes, void **out);
+WD_API int wd_host_free(void *p);
+/* Number of kernel launches issued by this context so far (bench.py gpu_launches). */
+WD_API int wd_launch_count(wd_ctx *ctx, uint64_t *out);
+
+/* ---- stage 1: neighbourhood construction ----------------------------------
+ * Replaces yield_coords + get_indexes of prepare_cluster_indexes.py
+ * (:99-116, :38-78): K0 converts the .locs floats with the reference's float64
+ * formula, K1 bins the wells into a uniform grid of 128-px cells, K2 searches
+ * the 3x3 cells around each centre. */
+WD_API int wd_locs_load(wd_ctx *ctx, const float *xy /* n x 2 */, uint32_t n);
+/* parity hook: the integer pixel coordinates K0 produced (prepare_cluster_indexes.py:110-112) */
+WD_API int wd_locs_pixels(wd_ctx *ctx, int32_t *x /* n */, int32_t *y /* n */);
+/* Rings 1..levels around each centre, using the index window
+ * [c - window_lo, c + window_hi] (20000 / 20001 in the reference, :43,:52-67)
+ * and the distance bins of MAX_DISTS (:19,:61-63); indices ascend inside a
+ * level.  level_offsets has t*levels+1 entries; idx receives
+ * level_offsets[t*levels] entries.  If idx_cap is too small the call returns
+ * WD_E_CAPACITY with *n_idx set to the size needed.  If some ring is empty the
+ * call returns WD_E_RUNTIME and *first_empty = target*levels + level of the
+ * first such ring in sample order (UINT32_MAX otherwise). */
+WD_API int wd_ring_query(wd_ctx *ctx, const uint32_t *centres, uint32_t t, int levels,
+                  uint32_t window_lo, uint32_t window_hi,
+                  uint32_t *level_offsets, uint32_t *idx, size_t idx_cap,
+                  uint64_t *n_idx, uint32_t *first_empty);
+
+/* ---- target list ------------------------------------------------------------
+ * The CSR form of what target.py:load_targets returns (:6-40): centres[t],
+ * level_offsets[t*levels+1] into idx[], for rings 1..levels. */
+WD_API int wd_targets_load(wd_ctx *ctx, const uint32_t *centres, const uint32_t *level_offsets,
+                    const uint32_t *idx, uint32_t t, int levels);
+
+/* ---- stage 2: tile staging ----------------------------------------------------
+ * A tile slot holds the gunzipped planes of one tile in HBM.  Replaces the
+ * per-cycle slurp in Tile.get_seqs (bcl_direct_reader.py:200-216, :333-345,
+ * :300-301); gunzip itself stays on the host. */
+WD_API int wd_tile_begin(wd_ctx *ctx, int tile_slot, uint32_t n_clusters, int n_planes);
+/* body of the .filter file (header stripped): bit0 = pass filter (:222-253) */
+WD_API int wd_tile_put_filter(wd_ctx *ctx, int tile_slot, const uint8_t *bytes, uint32_t n);
+/* body of a gunzipped .bcl (4-byte count stripped); n must equal n_clusters (:333-338) */
+WD_API int wd_tile_put_bcl(wd_ctx *ctx, int tile_slot, int plane, const uint8_t *bytes, uint32_t n);
+/* one inflated CBCL tile block (:300-301); n_block = cluster count in the
+ * tile record (PF count when excluded != 0) */
+WD_API int wd_tile_put_cbcl(wd_ctx *ctx, int tile_slot, int plane, const uint8_t *nibbles,
+                     uint32_t usize, uint32_t n_block, int excluded);
+/* K3: filter byte -> rank among PF wells or -1 (Tile._get_filter_offsets, :222-253) */
+WD_API int wd_filter_offsets(wd_ctx *ctx, int tile_slot, int32_t *offsets /* n_clusters */,
+                      uint32_t *passing);
+/* K3+K4/K5: Tile.get_seqs (:158-220) for arbitrary wells.  plane_order[p] is
+ * the plane that supplies sequence position p.  codes[i*seq_len + p] is
+ * 0..3 = A,C,G,T or 4 = N; pf[i] is the QUAL_FLAG.  Out-of-range or negative
+ * indices give WD_E_INDEX. */
+WD_API int wd_get_seqs(wd_ctx *ctx, int tile_slot, const int64_t *indices, uint32_t n_idx,
+                const int32_t *plane_order, int seq_len, uint8_t *codes, uint8_t *pf);
+
+/* ---- stage 3: compare + count -------------------------------------------------
+ * Replaces the target / level / well loops of main() and the integer part of
+ * output_writer (count_well_duplicates.py:228-265, :65-106) for tile slots
+ * first_slot .. first_slot+n_tiles-1 against the loaded target list.
+ *   per_target   [n_tiles][t][1+2*levels] int32: valid, then (dups, wells) per
+ *                level -- the reference's lane_dupl structure; may be NULL.
+ *   tile_counters[n_tiles][1+5*levels] int64: Targets, then per level
+ *                Wells, Dups, Hit, AccO, AccI.
+ * edit_distance / hamming are -e / --hamming (:200, :257).
+ * mode: 0 = fused gather+compare kernel, 1 = two-pass (K4/K5 packed words in
+ * HBM, then K6).  Both give identical results. */
+WD_API int wd_count(wd_ctx *ctx, int first_slot, int n_tiles, const int32_t *plane_order, int seq_len,
+             int edit_distance, int hamming, int mode,
+             int32_t *per_target, int64_t *tile_counters);
+/* Same, but only enqueues the kernels: results stay on the device (see
+ * wd_counters_devptr) until wd_count_fetch. */
+WD_API int wd_count_async(wd_ctx *ctx, int first_slot, int n_tiles, const int32_t *plane_order,
+                   int seq_len, int edit_distance, int hamming, int mode, int want_per_target);
+WD_API int wd_count_fetch(wd_ctx *ctx, int32_t *per_target, int64_t *tile_counters);
+/* Duplicate pairs of the last two-pass wd_count (count_well_duplicates.py:258-262):
+ * rows of (tile, target ordinal, well, distance), in reference log order. */
+WD_API int wd_dup_pairs(wd_ctx *ctx, int32_t *rows /* cap x 4 */, size_t cap, uint64_t *n_rows);
+
+/* ---- multi-GPU ------------------------------------------------------------------
+ * K7: place this rank's tile counters into a zero-initialised
+ * [n_rows_total][1+5*levels] int64 device array (tile_row[i] = global row of
+ * local tile i, lane_row[i] = row that accumulates its lane total) ready for one
+ * ncclAllReduce(int64, sum) issued by the host through torch.distributed.
+ * Replaces the cross-process "tail" concatenation of Snakefile.count_dups:146-151. */
+WD_API int wd_publish_counters(wd_ctx *ctx, const int32_t *tile_row, const int32_t *lane_row,
+                        int n_tiles, int n_rows_total, void **devptr, size_t *n_int64);
+WD_API int wd_counters_devptr(wd_ctx *ctx, void **devptr, size_t *n_int64);
+
+/* ---- exhaustive mode ---------------------------------------------------------------
+ * Every well of the tile is a target out to `levels` rings (BASELINE config 3):
+ * neighbours come straight from the stage-1 grid (no materialised target list),
+ * every well is packed once by a dense pass over the planes. */
+WD_API int wd_count_exhaustive(wd_ctx *ctx, int tile_slot, const int32_t *plane_order, int seq_len,
+                        int levels, uint32_t window_lo, uint32_t window_hi,
+                        int edit_distance, int hamming, int64_t *tile_counters);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WELLDUP_H */

@@ -1,0 +1,31 @@
+// TEST-ONLY host build of well_duplicates_b200/csrc/wd_seq.cuh so the packed
+// distance predicates can be checked against the oracle without a GPU.
+// Never linked into libwelldup.so.
+#include <stdint.h>
+#include "../well_duplicates_b200/csrc/wd_seq.cuh"
+
+template <int W>
+static void run(const uint8_t *a, const uint8_t *b, int len, int e, int ham, int *dup, int *exact, int *shd) {
+    wd::PSeq<W> pa, pb;
+    wd::pseq_clear(pa);
+    wd::pseq_clear(pb);
+    for (int i = 0; i < len; ++i) {
+        wd::pseq_set<W>(pa, i, a[i]);
+        wd::pseq_set<W>(pb, i, b[i]);
+    }
+    *dup = wd::is_duplicate<W>(pa, pb, len, e, ham != 0) ? 1 : 0;
+    *exact = ham ? wd::hamming<W>(pa, pb) : wd::myers_distance<W>(pa, pb, len);
+    *shd = wd::shd_rejects<W>(pa, pb, len, e) ? 1 : 0;
+}
+
+extern "C" int seq_check(const uint8_t *a, const uint8_t *b, int len, int words, int e, int ham,
+                         int *dup, int *exact, int *shd) {
+    switch (words) {
+        case 1: run<1>(a, b, len, e, ham, dup, exact, shd); return 0;
+        case 2: run<2>(a, b, len, e, ham, dup, exact, shd); return 0;
+        case 4: run<4>(a, b, len, e, ham, dup, exact, shd); return 0;
+        case 8: run<8>(a, b, len, e, ham, dup, exact, shd); return 0;
+        case 16: run<16>(a, b, len, e, ham, dup, exact, shd); return 0;
+    }
+    return -1;
+}

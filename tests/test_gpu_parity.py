@@ -1,0 +1,377 @@
+"""Parity of the CUDA path (through the C ABI and the Python mirrors of the
+reference interfaces) with the golden outputs of the unmodified reference and
+with the CPU oracle on seeded inputs.  Integer / byte work: everything is
+compared bit-exactly."""
+import contextlib
+import io
+import json
+import os
+
+import numpy as np
+import pytest
+
+import fixture_inputs as fx
+from helpers import GOLDEN, load_manifest, locs_path, parse_count_args
+
+pytestmark = pytest.mark.gpu
+MAN = load_manifest()
+
+
+@pytest.fixture(scope="module")
+def eng():
+    from well_duplicates_b200.reader import default_engine
+    return default_engine()
+
+
+@pytest.fixture(scope="module")
+def oracle():
+    from oracle import c_port, ref_port
+    return ref_port, c_port
+
+
+# ---------------------------------------------------------------- stage 1 --
+@pytest.mark.parametrize("name", sorted(fx.LOCS_FIXTURES))
+def test_k0_pixels(eng, oracle, name, tmp_path):
+    R, CP = oracle
+    _, xy = R.read_locs(locs_path(name, tmp_path))
+    eng.load_locs(xy)
+    x, y = eng.pixels()
+    X, Y = R.locs_to_pixels(xy)
+    assert np.array_equal(x, X) and np.array_equal(y, Y)
+
+
+@pytest.mark.parametrize("case", MAN["prepare"], ids=lambda c: "%s_n%d_s%s" % (c["locs"], c["n"], c["seed"]))
+def test_prepare_cli_byte_identical(case, tmp_path, capsys):
+    """prepare_cluster_indexes drop-in: stdout equals the reference's target file."""
+    from well_duplicates_b200 import prepare_cli
+    path = locs_path(case["locs"], tmp_path)
+    with open(os.path.join(GOLDEN, case["list"])) as fh:
+        want = fh.read()
+    argv = ["-f", path, "-n", str(case["n"])] + (["-s", str(case["seed"])] if case["seed"] is not None else [])
+    if case["returncode"] != 0:
+        with pytest.raises(RuntimeError, match="Got no wells"):
+            prepare_cli.main(argv)
+        assert capsys.readouterr().out == ""
+        return
+    prepare_cli.main(argv)
+    assert capsys.readouterr().out == want
+
+
+def test_ring_query_every_well_vs_oracle(eng, oracle, tmp_path):
+    """Every well of the shuffled lattice and a slice of the window lattice
+    against the oracle's scan (window rule, ordering, level bins)."""
+    R, CP = oracle
+    for name, centres in (("hex_shuffled", None), ("window_cm", list(range(19000, 19040)) + list(range(43900, 44000)) + [0, 1, 3999, 4000])):
+        _, xy = R.read_locs(locs_path(name, tmp_path))
+        X, Y = CP.locs_to_pixels(xy)
+        centres = list(range(xy.shape[0])) if centres is None else centres
+        eng.load_locs(xy)
+        offs, idx = eng.ring_query(centres, 5)
+        woffs, widx = CP.rings_csr(X, Y, centres)
+        assert np.array_equal(offs, woffs) and np.array_equal(idx, widx)
+
+
+def test_ring_query_fewer_levels_and_bad_centre(eng, oracle):
+    R, CP = oracle
+    _, xy = R.read_locs(locs_path("hex_small"))
+    X, Y = CP.locs_to_pixels(xy)
+    eng.load_locs(xy)
+    offs, idx = eng.ring_query([5, 1500], 2)
+    woffs, widx = CP.rings_csr(X, Y, [5, 1500], 2)
+    assert np.array_equal(offs, woffs) and np.array_equal(idx, widx)
+    with pytest.raises(IndexError):
+        eng.ring_query([xy.shape[0]], 5)
+
+
+# ---------------------------------------------------------------- stage 2 --
+@pytest.mark.parametrize("case", MAN["getseqs"], ids=lambda c: c["name"])
+def test_get_seqs_reader_api(case):
+    """BCLReader(...).get_tile(...).get_seqs(...) equals the reference's dict."""
+    from well_duplicates_b200.reader import BCLReader
+    with open(os.path.join(GOLDEN, "getseqs", case["name"] + ".json")) as fh:
+        want = json.load(fh)
+    tile = BCLReader(os.path.join(GOLDEN, case["run"])).get_tile(case["lane"], case["tile"])
+    if "error" in want:
+        with pytest.raises(IndexError):
+            tile.get_seqs(case["indices"], case["start"], case["end"])
+        return
+    got = tile.get_seqs(case["indices"], case["start"], case["end"])
+    assert {str(k): [v[0], v[1]] for k, v in got.items()} == want["ok"]
+    assert all(isinstance(k, int) and isinstance(v[1], bool) for k, v in got.items())
+
+
+def test_abi_rejects_out_of_range_wells(eng):
+    """The C entry point itself raises IndexError, not only the Python mirror."""
+    eng.tile_begin(0, 100, 1)
+    eng.tile_put_filter(0, np.ones(100, np.uint8))
+    eng.tile_put_bcl(0, 0, np.full(100, 5, np.uint8))
+    with pytest.raises(IndexError, match="out of range"):
+        eng.get_seqs(0, [3, 100], [0])
+    with pytest.raises(IndexError, match="negative"):
+        eng.get_seqs(0, [-2, 5], [0])
+    with pytest.raises(AssertionError):
+        eng.tile_put_bcl(0, 0, np.zeros(99, np.uint8))      # header mismatch, bcl_direct_reader.py:338
+
+
+@pytest.mark.parametrize("run,lane,tile", [("run_bcl", 1, 1101), ("run_cbcl", 1, 1102)])
+def test_k3_filter_offsets(oracle, run, lane, tile):
+    from well_duplicates_b200.reader import BCLReader
+    R, CP = oracle
+    t = BCLReader(os.path.join(GOLDEN, run)).get_tile(lane, tile)
+    got = t._get_filter_offsets()
+    want = R.filter_offsets(t.read_filter())
+    assert got == want.tolist() and t.passing_wells == int((want >= 0).sum())
+
+
+def test_k3_rank_large_random(eng, oracle):
+    R, CP = oracle
+    rng = np.random.default_rng(1)
+    for n in (1, 63, 64, 65, 4097, 1000003):
+        filt = rng.integers(0, 4, n, dtype=np.uint8)
+        eng.tile_begin(1, n, 0)
+        eng.tile_put_filter(1, filt)
+        off, passing = eng.filter_offsets(1)
+        woff, wpass = CP.filter_offsets(filt)
+        assert np.array_equal(off, woff) and passing == wpass
+
+
+# ---------------------------------------------------------------- stage 3 --
+@pytest.mark.parametrize("case", MAN["count"], ids=lambda c: c["name"])
+def test_count_cli_matches_reference(case):
+    """count_well_duplicates drop-in: stdout (report) and stderr (log with every
+    duplicate pair) equal the reference's."""
+    from well_duplicates_b200 import count_cli
+    with open(os.path.join(GOLDEN, "count", case["name"] + ".stdout")) as fh:
+        want_out = fh.read()
+    with open(os.path.join(GOLDEN, "count", case["name"] + ".stderr")) as fh:
+        want_err = fh.read()
+    argv = ["-f", os.path.join(GOLDEN, case["targets"]), "-r", os.path.join(GOLDEN, case["run"])] + case["args"]
+    out, err = io.StringIO(), io.StringIO()
+    with contextlib.redirect_stdout(out), contextlib.redirect_stderr(err):
+        if case["returncode"] != 0:
+            with pytest.raises(ZeroDivisionError):
+                count_cli.main(argv)
+        else:
+            count_cli.main(argv)
+    assert out.getvalue() == want_out
+    if case["returncode"] == 0:
+        assert err.getvalue() == want_err
+
+
+def _load_case(eng, R, case, o):
+    """Stage the golden run of a count case; returns (planes order, tiles, targets)."""
+    from well_duplicates_b200.reader import BCLReader
+    from well_duplicates_b200.targets import load_targets
+    targets = load_targets(os.path.join(GOLDEN, case["targets"]), levels=o["levels"] + 1, limit=o["limit"])
+    centres, offs, idx = targets.to_csr(o["levels"])
+    eng.load_targets(centres, offs, idx, o["levels"])
+    rd = BCLReader(os.path.join(GOLDEN, case["run"]), engine=eng)
+    wanted = [c for s, e in o["ranges"] for c in range(s, e)]
+    tiles = R.tile_list(o["stype"], o["tiles"])
+    lane = o["lanes"].split(",")[0]
+    for k, t in enumerate(tiles):
+        plane_of = rd.get_tile(lane, t).stage(k, wanted)
+    return [plane_of[c] for c in wanted], tiles, (centres, offs, idx), lane
+
+
+@pytest.mark.parametrize("name", ["lev_default", "hamming", "e4", "multirange", "long75_e3", "long140_hamming",
+                                  "cbcl_default", "cbcl_odd"])
+def test_fused_two_pass_and_oracle_agree(eng, oracle, name):
+    """Both kernel flavours, batched over the case's tiles, against the C oracle:
+    per-target (dups, wells) rows and the tile counters."""
+    R, CP = oracle
+    case = [c for c in MAN["count"] if c["name"] == name][0]
+    o = parse_count_args(case["args"])
+    order, tiles, (centres, offs, idx), lane = _load_case(eng, R, case, o)
+    pt0, c0 = eng.count(0, len(tiles), order, o["edit"], o["hamming"], mode=0)
+    pt1, c1 = eng.count(0, len(tiles), order, o["edit"], o["hamming"], mode=1)
+    assert np.array_equal(pt0, pt1) and np.array_equal(c0, c1)
+    run = os.path.join(GOLDEN, case["run"])
+    for k, t in enumerate(tiles):
+        planes, kinds = [], []
+        for s, e in o["ranges"]:
+            p, kd, filt, n = R.load_tile_planes(run, lane, t, s, e)
+            planes += p
+            kinds += kd
+        wpt, wc = CP.count_tile(planes, kinds, filt, centres, offs, idx, o["levels"], o["edit"], o["hamming"])
+        assert np.array_equal(pt0[k], wpt), (name, t)
+        assert np.array_equal(c0[k], wc), (name, t)
+
+
+def _synthetic_tile(seed, n_wells, row_len, n_cycles, n_targets, **kw):
+    from oracle import c_port as CP
+    from well_duplicates_b200 import synth
+    rng = np.random.default_rng(seed)
+    X, Y = synth.hex_lattice(n_wells, row_len)
+    td = synth.make_tile(rng, n_wells, n_cycles, row_len, **kw)
+    centres = rng.choice(n_wells, size=n_targets, replace=False).astype(np.uint32)
+    return X, Y, td, centres
+
+
+@pytest.mark.parametrize("e,ham", [(2, False), (2, True), (0, False), (3, False), (6, False), (60, False)])
+def test_medium_tile_vs_oracle(eng, oracle, e, ham):
+    """300 x 400 lattice, 50 cycles, 1500 targets: stage 1 on the GPU feeds
+    stages 2+3; everything checked against the C oracle."""
+    R, CP = oracle
+    from well_duplicates_b200 import synth
+    X, Y, td, centres = _synthetic_tile(7, 120000, 400, 50, 1500, dup_rate=0.2, shift_share=0.4, nocall_rate=0.03)
+    eng.load_locs(synth.xy_to_locs_floats(X, Y))
+    offs, idx = eng.ring_query(centres, 5)
+    woffs, widx = CP.rings_csr(X, Y, centres)
+    assert np.array_equal(offs, woffs) and np.array_equal(idx, widx)
+    eng.load_targets(centres, offs, idx, 5)
+    eng.tile_begin(0, td.n_wells, td.n_cycles)
+    eng.tile_put_filter(0, td.filt)
+    for c in range(td.n_cycles):
+        eng.tile_put_bcl(0, c, td.planes[c])
+    order = list(range(td.n_cycles))
+    wpt, wc = CP.count_tile([td.planes[c] for c in order], ["bcl"] * len(order), td.filt, centres, offs, idx, 5, e, ham)
+    for mode in (0, 1):
+        pt, cnt = eng.count(0, 1, order, e, ham, mode=mode)
+        assert np.array_equal(pt[0], wpt) and np.array_equal(cnt[0], wc)
+    assert wc[2::5].sum() > 50          # the case does contain duplicates
+
+
+def test_medium_cbcl_mixed_vs_oracle(eng, oracle):
+    """NovaSeq-style planes: first cycles store every well, later ones only PF
+    wells; odd PF count; three tiles in one launch."""
+    R, CP = oracle
+    from well_duplicates_b200 import synth
+    rng = np.random.default_rng(99)
+    n, row_len, ncyc, split = 50001, 250, 40, 17
+    X, Y = synth.hex_lattice(n, row_len)
+    centres = rng.choice(n, size=600, replace=False).astype(np.uint32)
+    woffs, widx = CP.rings_csr(X, Y, centres)
+    eng.load_targets(centres, woffs, widx, 5)
+    tiles = []
+    for k in range(3):
+        td = synth.make_tile(rng, n, ncyc, row_len, pf_rate=0.6, dup_rate=0.2, shift_share=0.3, nocall_rate=0.02)
+        pfmask = (td.filt & 1).astype(bool)
+        eng.tile_begin(k, n, ncyc)
+        eng.tile_put_filter(k, td.filt)
+        planes, kinds = [], []
+        for c in range(ncyc):
+            nib = synth.bcl_to_nibbles(td.planes[c])
+            excl = c >= split
+            if excl:
+                nib = nib[pfmask]
+            packed = synth.pack_nibbles(nib)
+            eng.tile_put_cbcl(k, c, packed, nib.size, excl)
+            planes.append(packed)
+            kinds.append("cbcl_excl" if excl else "cbcl")
+        tiles.append((planes, kinds, td.filt))
+    order = list(range(3, ncyc))
+    pt0, c0 = eng.count(0, 3, order, 2, False, mode=0)
+    pt1, c1 = eng.count(0, 3, order, 2, False, mode=1)
+    assert np.array_equal(pt0, pt1) and np.array_equal(c0, c1)
+    for k, (planes, kinds, filt) in enumerate(tiles):
+        wpt, wc = CP.count_tile([planes[c] for c in order], [kinds[c] for c in order], filt, centres, woffs, widx, 5, 2, False)
+        assert np.array_equal(pt0[k], wpt) and np.array_equal(c0[k], wc)
+    # a block whose cluster count disagrees with the filter is refused (cbcl_read.py:130-131)
+    eng.tile_put_cbcl(0, ncyc - 1, tiles[0][0][ncyc - 1], int((tiles[0][2] & 1).sum()) - 1, True)
+    with pytest.raises(AssertionError):
+        eng.count(0, 1, order, 2, False, mode=0)
+
+
+def test_dup_pair_log_rows(eng, oracle):
+    """Rows behind the stderr log: (tile, target, well, distance) in reference order."""
+    R, CP = oracle
+    case = [c for c in MAN["count"] if c["name"] == "long75_e3"][0]
+    o = parse_count_args(case["args"])
+    order, tiles, (centres, offs, idx), lane = _load_case(eng, R, case, o)
+    eng.count(0, len(tiles), order, o["edit"], o["hamming"], mode=1)
+    rows = eng.dup_pairs()
+    log = []
+    run = os.path.join(GOLDEN, case["run"])
+    targets = R.parse_target_file(os.path.join(GOLDEN, case["targets"]), levels=o["levels"] + 1, limit=o["limit"])
+    want = []
+    for k, t in enumerate(tiles):
+        seq_objs = [R.get_seqs_run(run, lane, t, R.all_indices(targets), s, e) for s, e in o["ranges"]]
+        log = []
+        R.count_tile(targets, seq_objs, o["levels"], o["edit"], o["hamming"], log)
+        want += [(k, c, w, d) for c, _, w, _, d in log]
+    got = [(int(r[0]), int(centres[r[1]]), int(r[2]), int(r[3])) for r in rows]
+    assert got == want and len(got) > 0
+
+
+def test_error_paths(eng):
+    with pytest.raises(ValueError):
+        eng.count(0, 1, [0] * 2000, 2, False)                 # longer than WD_MAX_SEQ_LEN
+    with pytest.raises(ValueError):
+        eng.count(50000, 1, [0], 2, False)                    # slot never begun
+    with pytest.raises(AssertionError):
+        eng.load_targets([5], [0, 2, 2], [1, 2], 2)           # empty ring, count_well_duplicates.py:249
+    eng.load_targets([5], [0, 2], [1, 200], 1)
+    eng.tile_begin(0, 100, 1)
+    eng.tile_put_filter(0, np.ones(100, np.uint8))
+    eng.tile_put_bcl(0, 0, np.full(100, 5, np.uint8))
+    with pytest.raises(IndexError):
+        eng.count(0, 1, [0], 2, False)                        # target well 200 on a 100-well tile
+
+
+# ------------------------------------------------------- full-size properties --
+@pytest.fixture(scope="module")
+def full_tile(eng):
+    """One HiSeq 4000 tile at BASELINE size: 4 309 650 wells, 50 cycles, 2500 targets."""
+    from well_duplicates_b200 import synth
+    n, row_len, ncyc = synth.HISEQ4000_WELLS, synth.HISEQ4000_ROW_LEN, 50
+    rng = np.random.default_rng(20261018)
+    X, Y = synth.hex_lattice(n, row_len)
+    td = synth.make_tile(rng, n, ncyc, row_len)
+    import random
+    random.seed(13)
+    centres = np.array(random.sample(range(n), 2500), dtype=np.uint32)
+    eng.load_locs(synth.xy_to_locs_floats(X, Y))
+    offs, idx = eng.ring_query(centres, 5)
+    eng.load_targets(centres, offs, idx, 5)
+    eng.tile_begin(0, n, ncyc)
+    eng.tile_put_filter(0, td.filt)
+    for c in range(ncyc):
+        eng.tile_put_bcl(0, c, td.planes[c])
+    return X, Y, td, centres, offs, idx
+
+
+def test_full_tile_stage1_vs_oracle(full_tile, oracle):
+    R, CP = oracle
+    X, Y, td, centres, offs, idx = full_tile
+    woffs, widx = CP.rings_csr(X, Y, centres[:400])
+    assert np.array_equal(offs[: woffs.size], woffs) and np.array_equal(idx[: widx.size], widx)
+    lens = np.diff(offs.astype(np.int64))
+    assert lens.min() >= 1
+    # ascending inside every ring
+    seg = np.repeat(np.arange(lens.size), lens)
+    d = np.diff(idx.astype(np.int64))
+    assert np.all(d[seg[1:] == seg[:-1]] > 0)
+
+
+@pytest.mark.parametrize("ham", [False, True])
+def test_full_tile_count_vs_oracle_and_properties(eng, full_tile, oracle, ham):
+    R, CP = oracle
+    X, Y, td, centres, offs, idx = full_tile
+    order = list(range(50))
+    pt0, c0 = eng.count(0, 1, order, 2, ham, mode=0)
+    pt1, c1 = eng.count(0, 1, order, 2, ham, mode=1)
+    assert np.array_equal(pt0, pt1) and np.array_equal(c0, c1)                       # two kernels, one answer
+    pt2, c2 = eng.count(0, 1, order, 2, ham, mode=0)
+    assert np.array_equal(pt0, pt2) and np.array_equal(c0, c2)                       # idempotent
+    wpt, wc = CP.count_tile([td.planes[c] for c in order], ["bcl"] * 50, td.filt, centres, offs, idx, 5, 2, ham)
+    assert np.array_equal(pt0[0], wpt) and np.array_equal(c0[0], wc)                 # the oracle
+    valid = pt0[0][:, 0] == 1
+    assert np.array_equal(valid, (td.filt[centres] & 1) == 1)                        # centre PF rule
+    assert c0[0][0] == valid.sum()
+    lens = np.diff(offs.astype(np.int64)).reshape(-1, 5)
+    assert np.array_equal(c0[0][1::5], lens[valid].sum(axis=0))                      # Wells = ring sizes of valid targets
+    assert np.array_equal(c0[0][2::5], pt0[0][:, 1::2].sum(axis=0))                  # Dups = sum of tallies
+    assert c0[0][4 + 5 * 4] == c0[0][5] == (pt0[0][:, 1::2].sum(axis=1) > 0).sum()   # AccO[5] == AccI[1] == any hit
+
+
+def test_full_tile_monotone_in_e(eng, full_tile):
+    order = list(range(50))
+    prev = None
+    for e in (0, 1, 2, 3, 5):
+        pt, _ = eng.count(0, 1, order, e, False, mode=0)
+        ph, _ = eng.count(0, 1, order, e, True, mode=0)
+        assert np.all(pt[0][:, 1::2] >= ph[0][:, 1::2])                              # Lev <= Ham
+        if prev is not None:
+            assert np.all(pt[0][:, 1::2] >= prev)
+        prev = pt[0][:, 1::2]

@@ -1,0 +1,83 @@
+"""The packed-sequence predicates of csrc/wd_seq.cuh (Hamming, shifted-Hamming
+filter, multi-word Myers) built for the host and checked against the oracle's
+textbook dynamic programme.  Host build is test infrastructure only."""
+import ctypes
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+from oracle import ref_port as R
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+
+
+@pytest.fixture(scope="module")
+def harness(tmp_path_factory):
+    so = str(tmp_path_factory.mktemp("seq") / "seq_harness.so")
+    subprocess.check_call(["g++", "-O2", "-std=c++17", "-shared", "-fPIC", "-o", so,
+                           os.path.join(HERE, "cpu_seq_harness.cpp")])
+    lib = ctypes.CDLL(so)
+    lib.seq_check.argtypes = [ctypes.c_char_p, ctypes.c_char_p] + [ctypes.c_int] * 4 + [ctypes.POINTER(ctypes.c_int)] * 3
+    return lib
+
+
+def check(lib, a, b, e, ham, words):
+    d, x, s = ctypes.c_int(), ctypes.c_int(), ctypes.c_int()
+    assert lib.seq_check(bytes(a), bytes(b), len(a), words, e, ham, d, x, s) == 0
+    return d.value, x.value, s.value
+
+
+def words_for(n):
+    for w in (1, 2, 4, 8, 16):
+        if n <= 64 * w:
+            return w
+    raise ValueError(n)
+
+
+def mutate(rng, a):
+    b = list(a)
+    for _ in range(int(rng.integers(0, 5))):
+        op = int(rng.integers(0, 3))
+        if op == 0 and b:
+            b[int(rng.integers(0, len(b)))] = int(rng.integers(0, 5))
+        elif op == 1 and b:
+            del b[int(rng.integers(0, len(b)))]
+            b.append(int(rng.integers(0, 5)))
+        else:
+            b.insert(int(rng.integers(0, len(b) + 1)), int(rng.integers(0, 5)))
+            b.pop()
+    return b
+
+
+@pytest.mark.parametrize("lengths", [(1, 20), (40, 64), (65, 130), (190, 260), (500, 520)])
+def test_predicates_match_oracle(harness, lengths):
+    rng = np.random.default_rng(lengths[0])
+    n_cases = 400 if lengths[1] < 200 else 60
+    for _ in range(n_cases):
+        n = int(rng.integers(lengths[0], lengths[1] + 1))
+        a = [int(v) for v in rng.integers(0, 5, n)]
+        b = mutate(rng, a) if rng.random() < 0.7 else [int(v) for v in rng.integers(0, 5, n)]
+        sa = "".join("ACGTN"[v] for v in a)
+        sb = "".join("ACGTN"[v] for v in b)
+        lev, hd = R.levenshtein(sa, sb), R.hamming(sa, sb)
+        w = words_for(n)
+        for e in (0, 1, 2, 3, 4, 7, n, n + 3):
+            d, x, s = check(harness, a, b, e, 0, w)
+            assert x == lev, (sa, sb)
+            assert d == int(lev <= e), (sa, sb, e)
+            assert not (s and lev <= e), "shifted-Hamming filter rejected a true duplicate"
+            d, x, _ = check(harness, a, b, e, 1, w)
+            assert x == hd and d == int(hd <= e)
+
+
+def test_wider_word_count_gives_same_answer(harness):
+    rng = np.random.default_rng(3)
+    for _ in range(100):
+        n = int(rng.integers(1, 64))
+        a = [int(v) for v in rng.integers(0, 5, n)]
+        b = mutate(rng, a)
+        ref = check(harness, a, b, 2, 0, 1)
+        for w in (2, 4, 16):
+            assert check(harness, a, b, 2, 0, w) == ref

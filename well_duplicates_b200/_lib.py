@@ -1,0 +1,88 @@
+"""ctypes binding of libwelldup.so (include/welldup.h).
+
+There is no CPU fallback: if the shared library has not been built, or no CUDA
+device is usable, the functions here raise."""
+import ctypes as C
+import os
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(HERE, "libwelldup.so")
+
+WD_OK = 0
+WD_E_INDEX, WD_E_RUNTIME, WD_E_ASSERT, WD_E_CUDA, WD_E_ARG, WD_E_CAPACITY = -1, -2, -3, -4, -5, -6
+PLANE_EMPTY, PLANE_BCL, PLANE_CBCL, PLANE_CBCL_EXCL = 0, 1, 2, 3
+MAX_LEVELS = 15
+MAX_SEQ_LEN = 1024
+
+
+class CudaError(RuntimeError):
+    """The CUDA runtime reported a failure (WD_E_CUDA)."""
+
+
+class CapacityError(RuntimeError):
+    """A caller-provided output array was too small (WD_E_CAPACITY)."""
+
+
+_EXC = {WD_E_INDEX: IndexError, WD_E_RUNTIME: RuntimeError, WD_E_ASSERT: AssertionError,
+        WD_E_CUDA: CudaError, WD_E_ARG: ValueError, WD_E_CAPACITY: CapacityError}
+
+_p = C.c_void_p
+_u8p, _i32p, _u32p, _i64p, _u64p, _f32p = (C.POINTER(t) for t in
+                                           (C.c_uint8, C.c_int32, C.c_uint32, C.c_int64, C.c_uint64, C.c_float))
+SIGNATURES = {
+    "wd_abi_version": (C.c_int, []),
+    "wd_last_error": (C.c_char_p, []),
+    "wd_create": (C.c_int, [C.c_int, C.POINTER(_p)]),
+    "wd_destroy": (C.c_int, [_p]),
+    "wd_set_stream": (C.c_int, [_p, _p]),
+    "wd_sync": (C.c_int, [_p]),
+    "wd_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_p)]),
+    "wd_host_free": (C.c_int, [_p]),
+    "wd_launch_count": (C.c_int, [_p, _u64p]),
+    "wd_locs_load": (C.c_int, [_p, _p, C.c_uint32]),
+    "wd_locs_pixels": (C.c_int, [_p, _p, _p]),
+    "wd_ring_query": (C.c_int, [_p, _p, C.c_uint32, C.c_int, C.c_uint32, C.c_uint32, _p, _p, C.c_size_t,
+                                _u64p, _u32p]),
+    "wd_targets_load": (C.c_int, [_p, _p, _p, _p, C.c_uint32, C.c_int]),
+    "wd_tile_begin": (C.c_int, [_p, C.c_int, C.c_uint32, C.c_int]),
+    "wd_tile_put_filter": (C.c_int, [_p, C.c_int, _p, C.c_uint32]),
+    "wd_tile_put_bcl": (C.c_int, [_p, C.c_int, C.c_int, _p, C.c_uint32]),
+    "wd_tile_put_cbcl": (C.c_int, [_p, C.c_int, C.c_int, _p, C.c_uint32, C.c_uint32, C.c_int]),
+    "wd_filter_offsets": (C.c_int, [_p, C.c_int, _p, _u32p]),
+    "wd_get_seqs": (C.c_int, [_p, C.c_int, _p, C.c_uint32, _p, C.c_int, _p, _p]),
+    "wd_count": (C.c_int, [_p, C.c_int, C.c_int, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p, _p]),
+    "wd_count_async": (C.c_int, [_p, C.c_int, C.c_int, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
+    "wd_count_fetch": (C.c_int, [_p, _p, _p]),
+    "wd_dup_pairs": (C.c_int, [_p, _p, C.c_size_t, _u64p]),
+    "wd_publish_counters": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, C.POINTER(_p), C.POINTER(C.c_size_t)]),
+    "wd_counters_devptr": (C.c_int, [_p, C.POINTER(_p), C.POINTER(C.c_size_t)]),
+    "wd_count_exhaustive": (C.c_int, [_p, C.c_int, _p, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_int, _p]),
+}
+
+_lib = None
+
+
+def load():
+    """dlopen the library (once).  Raises if it was never built."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise ImportError("%s is missing: build it with `python -m well_duplicates_b200.build` "
+                          "(nvcc, sm_100a). There is no CPU fallback." % LIB_PATH)
+    lib = C.CDLL(LIB_PATH)
+    for name, (res, args) in SIGNATURES.items():
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    if lib.wd_abi_version() != 1:
+        raise ImportError("libwelldup.so has ABI version %d, expected 1" % lib.wd_abi_version())
+    _lib = lib
+    return lib
+
+
+def check(rc):
+    if rc == WD_OK:
+        return
+    msg = load().wd_last_error().decode("utf-8", "replace")
+    raise _EXC.get(rc, RuntimeError)(msg)

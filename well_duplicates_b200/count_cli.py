@@ -1,0 +1,144 @@
+"""Command line of count_well_duplicates.py (reference :272-317) on the GPU.
+
+Same flags, defaults, stdout and stderr.  The host walks lanes and tiles, reads
+and inflates the files, and prints; the gather-decode, the distance tests and
+the counter reduction run in the CUDA library."""
+import re
+import sys
+from argparse import ArgumentDefaultsHelpFormatter, ArgumentParser
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+from . import reader as bcl_direct_reader
+from .report import dupl_from_per_target, output_writer
+from .targets import load_targets
+
+__VERSION__ = 0.3
+HISEQ_4000 = "hiseq_4000"
+HISEQ_X = "hiseq_x"
+HBM_BUDGET_BYTES = 120 << 30     # planes kept resident per batch of tiles
+
+
+def log(msg):
+    print(str(msg), file=sys.stderr)
+
+
+def parse_args(argv=None):
+    p = ArgumentParser(description="Counts well duplicates on a patterned flowcell without mapping: reads "
+                                   "within LEVEL rings of each sampled well are compared with it.",
+                       formatter_class=ArgumentDefaultsHelpFormatter)
+    p.add_argument("-f", "--coord_file", dest="coord_file", required=True, help="target list from prepare_cluster_indexes")
+    p.add_argument("-e", "--edit_distance", dest="edit_distance", type=int, default=2,
+                   help="largest distance that still counts as a duplicate")
+    p.add_argument("-n", "--sample_size", dest="sample_size", type=int, default=2500,
+                   help="number of targets to take from the list")
+    p.add_argument("-l", "--level", dest="level", type=int, default=3, help="rings around each centre to test, max = 5")
+    p.add_argument("-s", "--stype", dest="stype", required=True,
+                   help="%s, %s, or the highest tile number (e.g. 2228) from which swaths and tiles are inferred" % (HISEQ_4000, HISEQ_X))
+    p.add_argument("-r", "--run", dest="run", required=True, help="run folder (the one holding Data/)")
+    p.add_argument("-t", "--tile", dest="tile_id", type=str, help="comma-separated tiles or regexes, e.g. 1..[02468]")
+    p.add_argument("-i", "--lane", dest="lane", type=str, help="comma-separated lanes, 1-8")
+    p.add_argument("-x", "--start", dest="start", type=int, default=50, help="first cycle of the compared substring")
+    p.add_argument("-y", "--end", dest="end", type=int, default=100, help="cycle after the last one compared")
+    p.add_argument("--cycles", help="list of cycle ranges, e.g. 10-50,100-120; overrides -x/-y")
+    p.add_argument("--hamming", action="store_true", help="Hamming distance instead of Levenshtein")
+    p.add_argument("-S", "--summary-only", action="store_true", help="print only the per-lane summary")
+    p.add_argument("-q", "--quiet", action="store_true", help="no log output")
+    p.add_argument("--version", action="version", version=str(__VERSION__))
+    return p.parse_args(argv)
+
+
+def expected_tiles(stype, tile_id=None):
+    """Tile names of one lane (count_well_duplicates.py:164-191)."""
+    max_tile, max_swath = 24, 22
+    if stype == HISEQ_4000:
+        max_tile = 28
+    else:
+        try:
+            max_tile = int(stype) % 100
+            max_swath = int(stype) // 100 or 22
+        except ValueError:
+            pass
+    tiles = ["%d%d%02d" % (surface, swath, t)
+             for surface in range(1, max_swath // 10 + 1)
+             for swath in range(1, max_swath % 10 + 1)
+             for t in range(1, max_tile + 1)]
+    if tile_id:
+        keep = set()
+        for pat in tile_id.split(","):
+            hits = [t for t in tiles if re.match("^" + pat + "$", t)]
+            # the reference means to assert here but trips over an undefined name (:189)
+            assert hits, "%s matches no tile identifiers for a %s" % (pat, stype)
+            keep.update(hits)
+        tiles = sorted(keep)
+    return tiles
+
+
+def parse_cycles(args):
+    if args.cycles:
+        return [(int(s), int(e)) for r in args.cycles.split(",") for s, e in (r.split("-"),)]
+    return [(args.start, args.end)]
+
+
+def main(argv=None):
+    args = parse_args(argv)
+    say = (lambda *a: None) if args.quiet else log
+    lanes = args.lane.split(",") if args.lane else range(1, 8 + 1)
+    tiles = expected_tiles(args.stype, args.tile_id)
+    cycles = parse_cycles(args)
+    targets = load_targets(filename=args.coord_file, levels=args.level + 1, limit=args.sample_size)
+    bcl_reader = bcl_direct_reader.BCLReader(args.run)
+    eng = bcl_reader.engine
+    centres, level_offsets, idx = targets.to_csr(args.level)
+    eng.load_targets(centres, level_offsets, idx, args.level)
+    n_unique = len(targets.get_all_indices())
+    wanted = [c for s, e in cycles for c in range(s, e)]
+    # the duplicate-pair log needs the two-pass kernels and per-tile ordering on stderr
+    mode = 0 if args.quiet else 1
+    pool = ThreadPoolExecutor(max_workers=8)
+
+    for lane in lanes:
+        lane_dupl = {}
+        batch = []      # (tile name, slot)
+
+        def flush():
+            if not batch:
+                return
+            per_target, _ = eng.count(0, len(batch), [plane_of[c] for c in wanted], args.edit_distance,
+                                      args.hamming, mode=mode, per_target=True)
+            pairs = eng.dup_pairs() if mode == 1 else ()
+            for k, (tname, tile_obj) in enumerate(batch):
+                lane_dupl[tname] = dupl_from_per_target(per_target[k], args.level)
+                rows = [r for r in pairs if r[0] == k]
+                if rows:
+                    wells = sorted({int(centres[r[1]]) for r in rows} | {int(r[2]) for r in rows})
+                    codes, _ = eng.get_seqs(k, wells, [plane_of[c] for c in wanted])
+                    seq = dict(zip(wells, bcl_direct_reader.codes_to_strings(codes)))
+                    for _, t_ord, well, dist in rows:
+                        c = int(centres[t_ord])
+                        say("center seq at {:>07}: {}".format(c, seq[c]))
+                        say("well seq at   {:>07}: {}".format(int(well), seq[int(well)]))
+                        say("edit distance: {}".format(int(dist)))
+            batch.clear()
+
+        per_batch = 1
+        for tile in tiles:
+            say("Reading tile %s in lane %s" % (tile, lane))
+            tile_bcl = bcl_reader.get_tile(lane, tile)
+            if batch and batch[0][1].num_clusters != tile_bcl.num_clusters:
+                flush()         # one launch covers tiles of one size
+            plane_of = tile_bcl.stage(len(batch), wanted, pool)
+            if args.quiet:
+                tile_bytes = (tile_bcl.num_clusters + 256) * max(1, len(set(wanted)))
+                per_batch = max(1, min(4096, HBM_BUDGET_BYTES // tile_bytes))
+            say("Got %i sequences from %i contiguous cycle ranges." % (n_unique * len(cycles), len(cycles)))
+            batch.append((tile, tile_bcl))
+            if len(batch) >= per_batch:
+                flush()
+        flush()
+        output_writer(lane, len(targets), lane_dupl, verbose=not args.summary_only)
+
+
+if __name__ == "__main__":
+    main()

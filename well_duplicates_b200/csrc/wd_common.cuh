@@ -1,0 +1,140 @@
+// Internal declarations shared by the translation units of libwelldup.so.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+#include <vector>
+
+#include "../../include/welldup.h"
+
+namespace wd {
+
+// ---- error plumbing --------------------------------------------------------
+void set_error(const char *fmt, ...);
+#define WD_CUDA(call)                                                                      \
+    do {                                                                                   \
+        cudaError_t e__ = (call);                                                          \
+        if (e__ != cudaSuccess) {                                                          \
+            wd::set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__,             \
+                          cudaGetErrorString(e__));                                        \
+            return WD_E_CUDA;                                                              \
+        }                                                                                  \
+    } while (0)
+#define WD_TRY(call)                    \
+    do {                                \
+        int rc__ = (call);              \
+        if (rc__ != WD_OK) return rc__; \
+    } while (0)
+#define WD_FAIL(code, ...)           \
+    do {                             \
+        wd::set_error(__VA_ARGS__);  \
+        return (code);               \
+    } while (0)
+
+// ---- device buffer that only grows -------------------------------------------
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    int reserve(size_t bytes);   // keeps contents only when no reallocation happens
+    void release();
+    template <typename T>
+    T *as() const { return reinterpret_cast<T *>(p); }
+};
+
+// ---- one tile's planes in HBM ---------------------------------------------------
+struct TileDesc {                 // what the kernels see (array in device memory)
+    const uint8_t *planes;        // n_planes x stride bytes
+    unsigned long long stride;    // bytes between planes (multiple of 256)
+    const uint8_t *filter;        // n bytes, bit0 = PF
+    const uint64_t *pfmask;       // ceil(n/64) words: PF bit per well      (K3)
+    const uint32_t *pfrank;       // ceil(n/64) words: #PF wells before block (K3)
+    const uint8_t *kind;          // n_planes bytes: WD_PLANE_*
+    uint32_t n;                   // wells on the tile
+    uint32_t flags;               // bit0: pfmask / pfrank are valid
+};
+
+struct TileSlot {
+    uint32_t n = 0;
+    int n_planes = 0;
+    size_t stride = 0;
+    DevBuf planes, filter, pfmask, pfrank, kind_dev, pfcount_dev;
+    std::vector<uint8_t> kind;
+    std::vector<uint32_t> n_block;
+    bool filter_set = false;
+    bool rank_valid = false;
+    bool kind_dirty = true;
+    bool has_excl = false;
+};
+
+// ---- target list on the device ------------------------------------------------------
+// Slots are the wells of all targets laid out target after target: the centre
+// first, then the ring wells sorted by well index (so that consecutive lanes
+// read neighbouring bytes of a plane); slot_level says which ring a slot
+// belongs to, slot_csr where it sat in the caller's CSR (reference order).
+struct TargetList {
+    uint32_t t = 0;
+    int levels = 0;
+    uint32_t n_slots = 0;
+    uint32_t max_well = 0;
+    DevBuf tgt_off;      // u32 [t+1]
+    DevBuf slot_well;    // u32 [n_slots]
+    DevBuf slot_level;   // u8  [n_slots]
+    DevBuf slot_csr;     // u32 [n_slots]  (centre: UINT32_MAX)
+    DevBuf level_len;    // u32 [t*levels] wells per ring (LENGTH of the reference)
+    std::vector<uint32_t> h_idx;   // host copy of the caller's idx[] (duplicate-pair log)
+};
+
+}  // namespace wd
+
+struct wd_ctx {
+    int device = 0;
+    cudaStream_t own_stream = nullptr;
+    cudaStream_t stream = nullptr;
+    int sm_count = 148;
+    uint64_t launches = 0;
+
+    // stage 1
+    uint32_t n_locs = 0;
+    wd::DevBuf xy, px, py, bbox, cell_start, cell_cursor, cell_wells, scan_tmp;
+    int grid_w = 0, grid_h = 0, min_x = 0, min_y = 0;
+    wd::DevBuf q_centres, q_counts, q_offsets, q_idx, q_tmp, q_flag;
+    uint32_t q_t = 0;
+    int q_levels = 0;
+    uint64_t q_total = 0;
+
+    // stage 2/3
+    std::vector<wd::TileSlot> slots;
+    wd::TargetList targets;
+    wd::DevBuf descs, order_dev, packed, per_target, counters, publish, dup_rows, dup_count;
+    wd::DevBuf gs_idx, gs_packed, gs_codes;
+    wd::DevBuf x_packed, x_counts;   // exhaustive mode
+    // last count
+    int last_tiles = 0, last_levels = 0, last_first_slot = 0;
+    uint32_t last_t = 0;
+    bool last_per_target = false;
+    size_t publish_n = 0;
+    size_t dup_cap = 0;
+};
+
+namespace wd {
+
+// stage 1 (wd_stage1.cu)
+int locs_load(wd_ctx *ctx, const float *xy, uint32_t n);
+int ring_query(wd_ctx *ctx, const uint32_t *centres, uint32_t t, int levels, uint32_t wlo,
+               uint32_t whi, uint32_t *level_offsets, uint32_t *idx, size_t idx_cap,
+               uint64_t *n_idx, uint32_t *first_empty);
+
+// stage 2/3 (wd_stage23.cu)
+int filter_rank(wd_ctx *ctx, const int *slot_ids, int n);
+int filter_offsets(wd_ctx *ctx, int slot, int32_t *offsets, uint32_t *passing);
+int get_seqs(wd_ctx *ctx, int slot, const int64_t *indices, uint32_t n_idx, const int32_t *order,
+             int seq_len, uint8_t *codes, uint8_t *pf);
+int count_async(wd_ctx *ctx, int first_slot, int n_tiles, const int32_t *order, int seq_len, int e,
+                int hamming, int mode, int want_per_target);
+int publish_counters(wd_ctx *ctx, const int32_t *tile_row, const int32_t *lane_row, int n_tiles,
+                     int n_rows_total);
+int count_exhaustive(wd_ctx *ctx, int slot, const int32_t *order, int seq_len, int levels,
+                     uint32_t wlo, uint32_t whi, int e, int hamming, int64_t *tile_counters);
+int upload_descs(wd_ctx *ctx, int first_slot, int n_tiles);
+}  // namespace wd

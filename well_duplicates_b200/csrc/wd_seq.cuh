@@ -1,0 +1,212 @@
+// Packed base-call sequences and the distance predicates on them.
+//
+// A well's compared substring (<= 64*W symbols over {A,C,G,T,N}) is held as
+// three bit-planes of W 64-bit words: lo = bit0 of the base, hi = bit1 of the
+// base, nn = "is N".  Where nn is set, lo and hi are zero (canonical form), so
+// symbol equality is plain bitwise equality of the three planes and "N is an
+// ordinary character" (count_well_duplicates.py:238,251-252) comes for free.
+// Bits at positions >= len are zero in all planes.
+//
+// The functions compile for the device (nvcc) and for the host (g++), the
+// latter only so tests/ can drive them exhaustively against the oracle without
+// a GPU (tests/cpu_seq_harness.cpp); the library never calls them on the host.
+#pragma once
+#include <stdint.h>
+
+#if defined(__CUDACC__)
+#define WD_HD __host__ __device__ __forceinline__
+#else
+#define WD_HD inline
+#endif
+
+namespace wd {
+
+WD_HD int popc64(uint64_t v) {
+#if defined(__CUDA_ARCH__)
+    return __popcll(v);
+#else
+    return __builtin_popcountll(v);
+#endif
+}
+
+template <int W>
+struct PSeq {
+    uint64_t lo[W], hi[W], nn[W];
+};
+
+// valid-bit mask of word w for a sequence of len symbols
+WD_HD uint64_t len_mask(int len, int w) {
+    int rem = len - 64 * w;
+    if (rem >= 64) return ~0ull;
+    if (rem <= 0) return 0ull;
+    return (1ull << rem) - 1ull;
+}
+
+template <int W>
+WD_HD void pseq_clear(PSeq<W> &s) {
+#pragma unroll
+    for (int w = 0; w < W; ++w) s.lo[w] = s.hi[w] = s.nn[w] = 0ull;
+}
+
+// code: 0..3 = A,C,G,T; 4 = N
+template <int W>
+WD_HD void pseq_set(PSeq<W> &s, int pos, unsigned code) {
+    const int w = pos >> 6;
+    const int b = pos & 63;
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        if (i == w) {
+            s.lo[i] |= (uint64_t)(code & 1u) << b;
+            s.hi[i] |= (uint64_t)((code >> 1) & 1u) << b;
+            s.nn[i] |= (uint64_t)(code >> 2) << b;
+        }
+    }
+}
+
+template <int W>
+WD_HD unsigned pseq_get(const PSeq<W> &s, int pos) {
+    const int w = pos >> 6;
+    const int b = pos & 63;
+    uint64_t lo = 0, hi = 0, nn = 0;
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        if (i == w) { lo = s.lo[i]; hi = s.hi[i]; nn = s.nn[i]; }
+    }
+    return (unsigned)((lo >> b) & 1u) | ((unsigned)((hi >> b) & 1u) << 1) | ((unsigned)((nn >> b) & 1u) << 2);
+}
+
+// Positional mismatches (Levenshtein.hamming on equal-length strings,
+// count_well_duplicates.py:200).
+template <int W>
+WD_HD int hamming(const PSeq<W> &a, const PSeq<W> &b) {
+    int d = 0;
+#pragma unroll
+    for (int w = 0; w < W; ++w)
+        d += popc64((a.lo[w] ^ b.lo[w]) | (a.hi[w] ^ b.hi[w]) | (a.nn[w] ^ b.nn[w]));
+    return d;
+}
+
+// word w of the W-word bit string p shifted so that result[j] = p[j + d]
+// (zeros shifted in); |d| < 64.
+template <int W>
+WD_HD uint64_t shifted_word(const uint64_t *p, int w, int d) {
+    if (d == 0) return p[w];
+    if (d > 0) {
+        uint64_t v = p[w] >> d;
+        if (w + 1 < W) v |= p[w + 1] << (64 - d);
+        return v;
+    }
+    const int s = -d;
+    uint64_t v = p[w] << s;
+    if (w > 0) v |= p[w - 1] >> (64 - s);
+    return v;
+}
+
+// Shifted-Hamming lower bound.  In any edit script of cost <= e between two
+// strings of equal length, #insertions == #deletions <= k = e/2, so a symbol
+// of b that the script matches exactly is matched to a[j+d] for some
+// |d| <= k; every other symbol of b costs at least one edit.  Hence the
+// number of positions j with a[j+d] != b[j] for ALL |d| <= k is <= e whenever
+// Lev(a,b) <= e.  Returns true when that bound proves Lev(a,b) > e.
+template <int W>
+WD_HD bool shd_rejects(const PSeq<W> &a, const PSeq<W> &b, int len, int e) {
+    const int k = e >> 1;
+    if (k >= 64) return false;
+    int bad = 0;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        const uint64_t lm = len_mask(len, w);
+        if (lm == 0ull) break;
+        uint64_t all = lm;
+        for (int d = -k; d <= k; ++d) {
+            uint64_t mm = (shifted_word<W>(a.lo, w, d) ^ b.lo[w]) |
+                          (shifted_word<W>(a.hi, w, d) ^ b.hi[w]) |
+                          (shifted_word<W>(a.nn, w, d) ^ b.nn[w]);
+            // positions whose partner j+d falls outside [0, len) cannot match
+            if (d > 0) {
+                // j >= len - d
+                const int cut = len - d - 64 * w;   // first invalid bit in this word
+                if (cut <= 0) mm = ~0ull;
+                else if (cut < 64) mm |= ~((1ull << cut) - 1ull);
+            } else if (d < 0) {
+                // j < -d
+                const int cut = -d - 64 * w;        // bits [0, cut) invalid
+                if (cut >= 64) mm = ~0ull;
+                else if (cut > 0) mm |= (1ull << cut) - 1ull;
+            }
+            all &= mm;
+        }
+        bad += popc64(all);
+    }
+    return bad > e;
+}
+
+// Exact unit-cost edit distance between two equal-length packed strings
+// (Levenshtein.distance, count_well_duplicates.py:200,252): Myers' bit-vector
+// algorithm in Hyyro's global-alignment formulation, block-wise over W words
+// with the horizontal delta carried between blocks.
+template <int W>
+WD_HD int myers_distance(const PSeq<W> &a, const PSeq<W> &b, int len) {
+    if (len <= 0) return 0;
+    uint64_t Pv[W], Mv[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) { Pv[w] = ~0ull; Mv[w] = 0ull; }
+    const int last_w = (len - 1) >> 6;
+    const uint64_t last_bit = 1ull << ((len - 1) & 63);
+    int score = len;
+    for (int j = 0; j < len; ++j) {
+        const unsigned c = pseq_get<W>(b, j);
+        const uint64_t tlo = (c & 1u) ? ~0ull : 0ull;
+        const uint64_t thi = (c & 2u) ? ~0ull : 0ull;
+        const uint64_t tn = (c & 4u) ? ~0ull : 0ull;
+        int hin = 1;
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+            if (w <= last_w) {
+                uint64_t Eq = (tn & a.nn[w]) | (~tn & ~a.nn[w] & ~(a.lo[w] ^ tlo) & ~(a.hi[w] ^ thi));
+                const uint64_t pv = Pv[w], mv = Mv[w];
+                const uint64_t Xv = Eq | mv;
+                if (hin < 0) Eq |= 1ull;
+                const uint64_t Xh = (((Eq & pv) + pv) ^ pv) | Eq;
+                uint64_t Ph = mv | ~(Xh | pv);
+                uint64_t Mh = pv & Xh;
+                const uint64_t top = (w == last_w) ? last_bit : (1ull << 63);
+                int hout = 0;
+                if (Ph & top) hout = 1;
+                else if (Mh & top) hout = -1;
+                Ph <<= 1;
+                Mh <<= 1;
+                if (hin < 0) Mh |= 1ull;
+                else if (hin > 0) Ph |= 1ull;
+                Pv[w] = Mh | ~(Xv | Ph);
+                Mv[w] = Ph & Xv;
+                hin = hout;
+            }
+        }
+        score += hin;
+    }
+    return score;
+}
+
+// dist(a, b) <= e under the reference's chosen metric.
+template <int W>
+WD_HD bool is_duplicate(const PSeq<W> &a, const PSeq<W> &b, int len, int e, bool use_hamming) {
+    if (e < 0) return false;
+    const int ham = hamming<W>(a, b);
+    if (ham <= e) return true;                 // Lev <= Ham
+    if (use_hamming) return false;
+    if (e < 2) return false;                   // an indel pair costs 2: Lev <= 1 <=> Ham <= 1
+    if (e >= len) return true;                 // len substitutions always suffice
+    if (shd_rejects<W>(a, b, len, e)) return false;
+    return myers_distance<W>(a, b, len) <= e;
+}
+
+// the value the reference logs for a duplicate pair (count_well_duplicates.py:262)
+template <int W>
+WD_HD int exact_distance(const PSeq<W> &a, const PSeq<W> &b, int len, bool use_hamming) {
+    const int ham = hamming<W>(a, b);
+    if (use_hamming || ham <= 2) return ham;   // beating Ham needs an indel pair (2) replacing >= 3 mismatches
+    return myers_distance<W>(a, b, len);
+}
+
+}  // namespace wd

@@ -1,0 +1,716 @@
+// Stage 2 (K3 filter rank, K4/K5 gather-decode) and stage 3 (K6 compare +
+// count, K7 publish), plus the fused gather+compare kernel that is the
+// production path of wd_count.
+//
+// Reference semantics restated here:
+//  * PF flag = filter byte & 1; offset = rank among PF wells
+//    (bcl_direct_reader.py:222-253)
+//  * BCL call: byte 0 -> N, else base = byte & 3 (:352-354)
+//  * CBCL call: well w (or its PF rank when the block excludes non-PF wells,
+//    rank -1 -> N) -> low nibble if w even else high; nibble 0 -> N, else
+//    base = nibble & 3 (:303-325)
+//  * a target counts only if its centre is PF; ring wells are not PF-checked;
+//    N is an ordinary symbol (count_well_duplicates.py:236-262)
+//  * per-tile counters as output_writer sums them (:65-106)
+#include "wd_common.cuh"
+#include "wd_scan.cuh"
+#include "wd_seq.cuh"
+
+namespace wd {
+
+constexpr int PACK_STRIDE = 4;   // u64 per 64-symbol word group in HBM: lo, hi, nn, meta (32 B)
+constexpr int MAX_ORDER = WD_MAX_SEQ_LEN;
+
+// ============================================================================
+// K3: filter bytes -> PF bit mask + block ranks
+// ============================================================================
+// one thread per 64 wells; the filter buffer is zero-padded to a multiple of 64
+__global__ void __launch_bounds__(256)
+filter_mask_kernel(const uint8_t *__restrict__ filt, uint32_t n_blocks, uint64_t *__restrict__ mask,
+                   uint32_t *__restrict__ cnt) {
+    const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
+    if (b >= n_blocks) return;
+    const uint4 *src = reinterpret_cast<const uint4 *>(filt + (size_t)b * 64);
+    uint64_t m = 0;
+#pragma unroll
+    for (int q = 0; q < 4; ++q) {
+        const uint4 v = __ldg(src + q);
+        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+            // bit0 of each of the 4 bytes -> 4 adjacent bits
+            const uint32_t bits = (((w[k] & 0x01010101u) * 0x01020408u) >> 24) & 0xFu;
+            m |= (uint64_t)bits << (q * 16 + k * 4);
+        }
+    }
+    mask[b] = m;
+    cnt[b] = (uint32_t)__popcll(m);
+}
+
+__device__ __forceinline__ int pf_rank(const TileDesc &d, uint32_t well) {
+    const uint64_t m = __ldg(d.pfmask + (well >> 6));
+    const int b = well & 63;
+    if (!((m >> b) & 1ull)) return -1;
+    return (int)(__ldg(d.pfrank + (well >> 6)) + (uint32_t)__popcll(m & ((1ull << b) - 1ull)));
+}
+
+// the reference's filter_offsets list (parity hook)
+__global__ void __launch_bounds__(256)
+filter_expand_kernel(TileDesc d, int32_t *__restrict__ out) {
+    const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < d.n) out[i] = pf_rank(d, i);
+}
+
+int filter_rank(wd_ctx *ctx, const int *slot_ids, int n) {
+    cudaStream_t st = ctx->stream;
+    for (int k = 0; k < n; ++k) {
+        TileSlot &s = ctx->slots[slot_ids[k]];
+        if (s.rank_valid) continue;
+        if (!s.filter_set) WD_FAIL(WD_E_ARG, "tile slot %d has no filter loaded", slot_ids[k]);
+        const uint32_t nb = (s.n + 63) / 64;
+        WD_TRY(s.pfmask.reserve((size_t)nb * 8));
+        WD_TRY(s.pfrank.reserve(((size_t)nb + 1) * 4));
+        WD_TRY(s.pfcount_dev.reserve((size_t)nb * 4));
+        WD_TRY(ctx->scan_tmp.reserve(scan_tmp_words(nb) * 4));
+        filter_mask_kernel<<<(nb + 255) / 256, 256, 0, st>>>(s.filter.as<uint8_t>(), nb, s.pfmask.as<uint64_t>(),
+                                                              s.pfcount_dev.as<uint32_t>());
+        ctx->launches++;
+        WD_CUDA(exclusive_scan_u32(s.pfcount_dev.as<uint32_t>(), s.pfrank.as<uint32_t>(), nb,
+                                   ctx->scan_tmp.as<uint32_t>(), st, &ctx->launches));
+        s.rank_valid = true;
+    }
+    return WD_OK;
+}
+
+static TileDesc make_desc(const TileSlot &s) {
+    TileDesc d;
+    d.planes = s.planes.as<uint8_t>();
+    d.stride = s.stride;
+    d.filter = s.filter.as<uint8_t>();
+    d.pfmask = s.pfmask.as<uint64_t>();
+    d.pfrank = s.pfrank.as<uint32_t>();
+    d.kind = s.kind_dev.as<uint8_t>();
+    d.n = s.n;
+    d.flags = s.rank_valid ? 1u : 0u;
+    return d;
+}
+
+int filter_offsets(wd_ctx *ctx, int slot, int32_t *offsets, uint32_t *passing) {
+    TileSlot &s = ctx->slots[slot];
+    WD_TRY(filter_rank(ctx, &slot, 1));
+    cudaStream_t st = ctx->stream;
+    WD_TRY(ctx->gs_codes.reserve((size_t)s.n * 4));
+    filter_expand_kernel<<<(s.n + 255) / 256, 256, 0, st>>>(make_desc(s), ctx->gs_codes.as<int32_t>());
+    ctx->launches++;
+    WD_CUDA(cudaGetLastError());
+    WD_CUDA(cudaMemcpyAsync(offsets, ctx->gs_codes.p, (size_t)s.n * 4, cudaMemcpyDeviceToHost, st));
+    uint32_t pf = 0;
+    WD_CUDA(cudaMemcpyAsync(&pf, s.pfrank.as<uint32_t>() + (s.n + 63) / 64, 4, cudaMemcpyDeviceToHost, st));
+    WD_CUDA(cudaStreamSynchronize(st));
+    if (passing) *passing = pf;
+    return WD_OK;
+}
+
+// ============================================================================
+// K4 / K5: gather-decode one well into packed words
+// ============================================================================
+// s_off[p]  = byte offset of the plane that supplies sequence position p
+// s_kind[p] = WD_PLANE_* of that plane (same for every tile of a launch)
+template <int W, bool ALL_BCL>
+__device__ __forceinline__ void decode_well(const TileDesc &d, uint32_t well, const unsigned long long *s_off,
+                                            const uint8_t *s_kind, int len, PSeq<W> &out) {
+    int rank = 0;
+    if (!ALL_BCL && (d.flags & 1u)) rank = pf_rank(d, well);
+    const uint8_t *base = d.planes;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        uint64_t lo = 0, hi = 0, nn = 0;
+        const int p0 = 64 * w;
+        const int cnt = min(64, len - p0);
+        for (int i0 = 0; i0 < cnt; i0 += 8) {
+            uint32_t code[8];
+            // issue the eight independent loads first (memory-level parallelism) ...
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const int p = p0 + i0 + j;
+                code[j] = 4u;                    // beyond the sequence: contributes no bit to any plane
+                if (i0 + j < cnt) {
+                    if (ALL_BCL) {
+                        code[j] = __ldg(base + s_off[p] + well);
+                    } else {
+                        const int kind = s_kind[p];
+                        if (kind == WD_PLANE_BCL) {
+                            code[j] = __ldg(base + s_off[p] + well);
+                        } else {
+                            const int wi = kind == WD_PLANE_CBCL_EXCL ? rank : (int)well;
+                            uint32_t nib = 0;
+                            if (wi >= 0) {
+                                const uint32_t byte = __ldg(base + s_off[p] + ((uint32_t)wi >> 1));
+                                nib = (wi & 1) ? (byte >> 4) : (byte & 15u);
+                            }
+                            code[j] = nib;       // nibble 0 -> N, like byte 0
+                        }
+                    }
+                }
+            }
+            // ... then fold them into 8-bit groups of the three planes:
+            // base = code & 3; code 0 (no-call) sets the N plane and no base bit
+            uint32_t glo = 0, ghi = 0, gnn = 0;
+#pragma unroll
+            for (int j = 0; j < 8; ++j) {
+                const uint32_t b = code[j];
+                glo |= (b & 1u) << j;
+                ghi |= ((b >> 1) & 1u) << j;
+                gnn |= (b == 0u ? 1u : 0u) << j;
+            }
+            lo |= (uint64_t)glo << i0;
+            hi |= (uint64_t)ghi << i0;
+            nn |= (uint64_t)gnn << i0;
+        }
+        // canonical form: N positions carry no base bits (true by construction: code 0)
+        out.lo[w] = lo;
+        out.hi[w] = hi;
+        out.nn[w] = nn;
+    }
+}
+
+template <int W>
+__device__ __forceinline__ void store_packed(uint64_t *dst, const PSeq<W> &s, uint64_t meta) {
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        ulonglong2 *q = reinterpret_cast<ulonglong2 *>(dst + (size_t)w * PACK_STRIDE);
+        q[0] = make_ulonglong2(s.lo[w], s.hi[w]);
+        q[1] = make_ulonglong2(s.nn[w], w == 0 ? meta : 0ull);
+    }
+}
+
+template <int W>
+__device__ __forceinline__ uint64_t load_packed(const uint64_t *src, PSeq<W> &s) {
+    uint64_t meta = 0;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        const ulonglong2 *q = reinterpret_cast<const ulonglong2 *>(src + (size_t)w * PACK_STRIDE);
+        const ulonglong2 a = q[0], b = q[1];
+        s.lo[w] = a.x; s.hi[w] = a.y; s.nn[w] = b.x;
+        if (w == 0) meta = b.y;
+    }
+    return meta;
+}
+
+__device__ __forceinline__ void load_order(const unsigned long long *g_off, const uint8_t *g_kind, int len,
+                                           unsigned long long *s_off, uint8_t *s_kind) {
+    for (int i = threadIdx.x; i < len; i += blockDim.x) {
+        s_off[i] = g_off[i];
+        s_kind[i] = g_kind[i];
+    }
+    __syncthreads();
+}
+
+// one thread per (tile, slot): packed[tile][slot][W][4]
+template <int W, bool ALL_BCL>
+__global__ void __launch_bounds__(256)
+gather_pack_kernel(const TileDesc *__restrict__ descs, const uint32_t *__restrict__ slot_well, uint32_t n_slots,
+                   const unsigned long long *__restrict__ g_off, const uint8_t *__restrict__ g_kind, int len,
+                   uint64_t *__restrict__ packed) {
+    __shared__ unsigned long long s_off[MAX_ORDER];
+    __shared__ uint8_t s_kind[MAX_ORDER];
+    load_order(g_off, g_kind, len, s_off, s_kind);
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_slots) return;
+    const TileDesc d = descs[blockIdx.y];
+    const uint32_t well = __ldg(slot_well + s);
+    PSeq<W> q;
+    decode_well<W, ALL_BCL>(d, well, s_off, s_kind, len, q);
+    const uint64_t meta = __ldg(d.filter + well) & 1u;
+    store_packed<W>(packed + ((size_t)blockIdx.y * n_slots + s) * (size_t)(W * PACK_STRIDE), q, meta);
+}
+
+// packed -> one byte per symbol (0..3 ACGT, 4 N) for wd_get_seqs
+template <int W>
+__global__ void __launch_bounds__(256)
+unpack_codes_kernel(const uint64_t *__restrict__ packed, uint32_t n_idx, int len, uint8_t *__restrict__ codes,
+                    uint8_t *__restrict__ pf) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_idx) return;
+    PSeq<W> q;
+    const uint64_t meta = load_packed<W>(packed + (size_t)s * (W * PACK_STRIDE), q);
+    pf[s] = (uint8_t)(meta & 1u);
+    for (int p = 0; p < len; ++p) {
+        const unsigned c = pseq_get<W>(q, p);
+        codes[(size_t)s * len + p] = (uint8_t)((c & 4u) ? 4u : c);
+    }
+}
+
+// ============================================================================
+// K6: compare + count
+// ============================================================================
+struct CountArgs {
+    const TileDesc *descs;
+    const uint32_t *tgt_off, *slot_well, *slot_csr, *level_len;
+    const uint8_t *slot_level;
+    const unsigned long long *g_off;
+    const uint8_t *g_kind;
+    const uint64_t *packed;          // two-pass only
+    int32_t *per_target;             // may be null
+    unsigned long long *counters;    // [tiles][1+5L]
+    int32_t *dup_rows;               // may be null: (tile, target, csr position, distance)
+    unsigned long long *dup_count;
+    unsigned long long dup_cap;
+    uint32_t t, n_slots;
+    int levels, len, e, hamming;
+};
+
+// Per-warp tallies -> per_target row and the CTA's shared counters.
+template <int LMAX>
+__device__ __forceinline__ void finish_target(const CountArgs &a, uint32_t tile, uint32_t t, int lane, bool valid,
+                                              const uint32_t *dups, uint32_t *s_cnt) {
+    const int L = a.levels;
+    const int row = 1 + 2 * L;
+    if (a.per_target != nullptr) {
+        int32_t *pt = a.per_target + ((size_t)tile * a.t + t) * row;
+        if (lane == 0) pt[0] = valid ? 1 : 0;
+#pragma unroll
+        for (int l = 0; l < LMAX; ++l) {
+            if (l < L && lane == l) {
+                pt[1 + 2 * l] = valid ? (int32_t)dups[l] : 0;
+                pt[2 + 2 * l] = valid ? (int32_t)__ldg(a.level_len + (size_t)t * L + l) : 0;
+            }
+        }
+    }
+    if (!valid) return;
+    // AccO: a hit at this level or further in; AccI: at this level or further out
+    // (count_well_duplicates.py:77-89)
+    uint32_t hit_mask = 0;
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l)
+        if (l < L && dups[l]) hit_mask |= 1u << l;
+    if (lane == 0) atomicAdd(&s_cnt[0], 1u);
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l) {
+        if (l < L && lane == l) {
+            uint32_t *c = s_cnt + 1 + 5 * l;
+            atomicAdd(c + 0, __ldg(a.level_len + (size_t)t * L + l));
+            if (dups[l]) {
+                atomicAdd(c + 1, dups[l]);
+                atomicAdd(c + 2, 1u);
+            }
+            if (hit_mask & ((2u << l) - 1u)) atomicAdd(c + 3, 1u);
+            if (hit_mask >> l) atomicAdd(c + 4, 1u);
+        }
+    }
+}
+
+template <int W>
+__device__ __forceinline__ void log_dup(const CountArgs &a, uint32_t tile, uint32_t t, uint32_t slot,
+                                        const PSeq<W> &c, const PSeq<W> &b) {
+    const unsigned long long pos = atomicAdd(a.dup_count, 1ull);
+    if (pos < a.dup_cap) {
+        int32_t *r = a.dup_rows + pos * 4;
+        r[0] = (int32_t)tile;
+        r[1] = (int32_t)t;
+        r[2] = (int32_t)__ldg(a.slot_csr + slot);
+        r[3] = exact_distance<W>(c, b, a.len, a.hamming != 0);
+    }
+}
+
+__device__ __forceinline__ void flush_counters(uint32_t *s_cnt, unsigned long long *dst, int n) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        if (s_cnt[i]) atomicAdd(dst + i, (unsigned long long)s_cnt[i]);
+}
+
+constexpr int CNT_WARPS = 8;
+
+// two-pass flavour: reads the packed words K4/K5 left in HBM.  One warp per
+// (tile, target); lanes stride over the target's ring slots.
+template <int W, int LMAX>
+__global__ void __launch_bounds__(CNT_WARPS * 32)
+compare_count_kernel(CountArgs a) {
+    __shared__ uint32_t s_cnt[1 + 5 * LMAX];
+    for (int i = threadIdx.x; i < 1 + 5 * LMAX; i += blockDim.x) s_cnt[i] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint32_t tile = blockIdx.y;
+    const uint32_t t = blockIdx.x * CNT_WARPS + (threadIdx.x >> 5);
+    if (t < a.t) {
+        const uint32_t s0 = __ldg(a.tgt_off + t), s1 = __ldg(a.tgt_off + t + 1);
+        const uint64_t *tp = a.packed + (size_t)tile * a.n_slots * (W * PACK_STRIDE);
+        PSeq<W> c;
+        const uint64_t meta = load_packed<W>(tp + (size_t)s0 * (W * PACK_STRIDE), c);
+        const bool valid = (meta & 1ull) != 0;
+        uint32_t dups[LMAX];
+#pragma unroll
+        for (int l = 0; l < LMAX; ++l) dups[l] = 0;
+        if (valid) {
+            for (uint32_t base = s0 + 1; base < s1; base += 32) {
+                const uint32_t s = base + lane;
+                bool dup = false;
+                int lvl = 0;
+                if (s < s1) {
+                    PSeq<W> b;
+                    load_packed<W>(tp + (size_t)s * (W * PACK_STRIDE), b);
+                    lvl = __ldg(a.slot_level + s);
+                    dup = is_duplicate<W>(c, b, a.len, a.e, a.hamming != 0);
+                    if (dup && a.dup_rows != nullptr) log_dup<W>(a, tile, t, s, c, b);
+                }
+#pragma unroll
+                for (int l = 0; l < LMAX; ++l)
+                    if (l < a.levels) dups[l] += __popc(__ballot_sync(0xffffffffu, dup && lvl == l + 1));
+            }
+        }
+        finish_target<LMAX>(a, tile, t, lane, valid, dups, s_cnt);
+    }
+    flush_counters(s_cnt, a.counters + (size_t)tile * (1 + 5 * a.levels), 1 + 5 * a.levels);
+}
+
+// fused flavour (production): the warp gathers and decodes its target's wells
+// straight from the planes, compares in registers and never writes the packed
+// words.  Targets whose centre fails the filter are skipped before any plane
+// byte is read.
+template <int W, int LMAX, bool ALL_BCL>
+__global__ void __launch_bounds__(CNT_WARPS * 32)
+fused_count_kernel(CountArgs a) {
+    __shared__ unsigned long long s_off[MAX_ORDER];
+    __shared__ uint8_t s_kind[MAX_ORDER];
+    __shared__ uint32_t s_cnt[1 + 5 * LMAX];
+    for (int i = threadIdx.x; i < 1 + 5 * LMAX; i += blockDim.x) s_cnt[i] = 0;
+    load_order(a.g_off, a.g_kind, a.len, s_off, s_kind);
+    const int lane = threadIdx.x & 31;
+    const uint32_t tile = blockIdx.y;
+    const uint32_t t = blockIdx.x * CNT_WARPS + (threadIdx.x >> 5);
+    if (t < a.t) {
+        const TileDesc d = a.descs[tile];
+        const uint32_t s0 = __ldg(a.tgt_off + t), s1 = __ldg(a.tgt_off + t + 1);
+        const uint32_t centre = __ldg(a.slot_well + s0);
+        const bool valid = (__ldg(d.filter + centre) & 1u) != 0;
+        uint32_t dups[LMAX];
+#pragma unroll
+        for (int l = 0; l < LMAX; ++l) dups[l] = 0;
+        if (valid) {
+            PSeq<W> c;
+            // first chunk: lane 0 decodes the centre, lanes 1..31 the first ring slots
+            for (uint32_t base = s0; base < s1; base += 32) {
+                const uint32_t s = base + lane;
+                PSeq<W> b;
+                pseq_clear(b);
+                int lvl = 0;
+                if (s < s1) {
+                    decode_well<W, ALL_BCL>(d, __ldg(a.slot_well + s), s_off, s_kind, a.len, b);
+                    lvl = __ldg(a.slot_level + s);
+                }
+                if (base == s0) {
+#pragma unroll
+                    for (int w = 0; w < W; ++w) {
+                        c.lo[w] = __shfl_sync(0xffffffffu, b.lo[w], 0);
+                        c.hi[w] = __shfl_sync(0xffffffffu, b.hi[w], 0);
+                        c.nn[w] = __shfl_sync(0xffffffffu, b.nn[w], 0);
+                    }
+                }
+                bool dup = false;
+                if (s < s1 && lvl > 0) dup = is_duplicate<W>(c, b, a.len, a.e, a.hamming != 0);
+#pragma unroll
+                for (int l = 0; l < LMAX; ++l)
+                    if (l < a.levels) dups[l] += __popc(__ballot_sync(0xffffffffu, dup && lvl == l + 1));
+            }
+        }
+        finish_target<LMAX>(a, tile, t, lane, valid, dups, s_cnt);
+    }
+    flush_counters(s_cnt, a.counters + (size_t)tile * (1 + 5 * a.levels), 1 + 5 * a.levels);
+}
+
+// ============================================================================
+// K7: place tile counters into the all-reduce buffer
+// ============================================================================
+__global__ void publish_kernel(const unsigned long long *__restrict__ counters, const int32_t *__restrict__ tile_row,
+                               const int32_t *__restrict__ lane_row, int n_tiles, int width,
+                               unsigned long long *__restrict__ out) {
+    const int i = blockIdx.x * blockDim.x + threadIdx.x;
+    if (i >= n_tiles * width) return;
+    const int tile = i / width, k = i % width;
+    const unsigned long long v = counters[i];
+    if (tile_row[tile] >= 0) out[(size_t)tile_row[tile] * width + k] = v;
+    if (lane_row[tile] >= 0 && v) atomicAdd(out + (size_t)lane_row[tile] * width + k, v);
+}
+
+// ============================================================================
+// host side
+// ============================================================================
+static int words_for(int len) {
+    if (len <= 64) return 1;
+    if (len <= 128) return 2;
+    if (len <= 256) return 4;
+    if (len <= 512) return 8;
+    return 16;
+}
+
+// plane order -> per-position byte offsets and kinds; checks that every tile
+// of the batch agrees on stride / kinds (they share one launch).
+static int prepare_order(wd_ctx *ctx, int first_slot, int n_tiles, const int32_t *order, int len, bool *all_bcl,
+                         bool *any_excl) {
+    if (len < 1 || len > WD_MAX_SEQ_LEN)
+        WD_FAIL(WD_E_ARG, "compared sequence length %d is outside 1..%d", len, WD_MAX_SEQ_LEN);
+    if (first_slot < 0 || n_tiles < 1 || (size_t)first_slot + n_tiles > ctx->slots.size())
+        WD_FAIL(WD_E_ARG, "tile slots %d..%d have not been begun", first_slot, first_slot + n_tiles - 1);
+    const TileSlot &s0 = ctx->slots[first_slot];
+    std::vector<unsigned long long> off(len);
+    std::vector<uint8_t> kind(len);
+    *all_bcl = true;
+    *any_excl = false;
+    for (int p = 0; p < len; ++p) {
+        const int pl = order[p];
+        if (pl < 0 || pl >= s0.n_planes) WD_FAIL(WD_E_ARG, "plane %d out of range (slot has %d planes)", pl, s0.n_planes);
+        off[p] = (unsigned long long)pl * s0.stride;
+        kind[p] = s0.kind[pl];
+        if (kind[p] == WD_PLANE_EMPTY) WD_FAIL(WD_E_ARG, "plane %d of tile slot %d was never loaded", pl, first_slot);
+        if (kind[p] != WD_PLANE_BCL) *all_bcl = false;
+        if (kind[p] == WD_PLANE_CBCL_EXCL) *any_excl = true;
+    }
+    for (int k = 0; k < n_tiles; ++k) {
+        const TileSlot &s = ctx->slots[first_slot + k];
+        if (s.n == 0 || !s.filter_set) WD_FAIL(WD_E_ARG, "tile slot %d is not fully loaded", first_slot + k);
+        if (s.stride != s0.stride || s.n_planes != s0.n_planes)
+            WD_FAIL(WD_E_ARG, "tile slots of one batch must have the same plane count and stride");
+        for (int p = 0; p < len; ++p)
+            if (s.kind[order[p]] != kind[p])
+                WD_FAIL(WD_E_ARG, "tile slot %d: plane %d has a different format than in slot %d", first_slot + k,
+                        order[p], first_slot);
+    }
+    cudaStream_t st = ctx->stream;
+    WD_TRY(ctx->order_dev.reserve((size_t)MAX_ORDER * 9));
+    WD_CUDA(cudaMemcpyAsync(ctx->order_dev.p, off.data(), (size_t)len * 8, cudaMemcpyHostToDevice, st));
+    WD_CUDA(cudaMemcpyAsync(ctx->order_dev.as<uint8_t>() + (size_t)MAX_ORDER * 8, kind.data(), (size_t)len,
+                            cudaMemcpyHostToDevice, st));
+    return WD_OK;
+}
+
+int upload_descs(wd_ctx *ctx, int first_slot, int n_tiles) {
+    std::vector<TileDesc> h(n_tiles);
+    cudaStream_t st = ctx->stream;
+    for (int k = 0; k < n_tiles; ++k) {
+        TileSlot &s = ctx->slots[first_slot + k];
+        if (s.kind_dirty) {
+            WD_TRY(s.kind_dev.reserve((size_t)s.n_planes));
+            WD_CUDA(cudaMemcpyAsync(s.kind_dev.p, s.kind.data(), (size_t)s.n_planes, cudaMemcpyHostToDevice, st));
+            s.kind_dirty = false;
+        }
+        h[k] = make_desc(s);
+    }
+    WD_TRY(ctx->descs.reserve((size_t)n_tiles * sizeof(TileDesc)));
+    WD_CUDA(cudaMemcpyAsync(ctx->descs.p, h.data(), (size_t)n_tiles * sizeof(TileDesc), cudaMemcpyHostToDevice, st));
+    return WD_OK;
+}
+
+template <int W, bool ALL_BCL>
+static void launch_gather(wd_ctx *ctx, const TileDesc *descs, const uint32_t *slot_well, uint32_t n_slots, int n_tiles,
+                          int len, uint64_t *packed) {
+    const unsigned long long *g_off = ctx->order_dev.as<unsigned long long>();
+    const uint8_t *g_kind = ctx->order_dev.as<uint8_t>() + (size_t)MAX_ORDER * 8;
+    dim3 grid((n_slots + 255) / 256, n_tiles);
+    gather_pack_kernel<W, ALL_BCL><<<grid, 256, 0, ctx->stream>>>(descs, slot_well, n_slots, g_off, g_kind, len, packed);
+    ctx->launches++;
+}
+
+template <int W>
+static void launch_gather_w(wd_ctx *ctx, bool all_bcl, const TileDesc *descs, const uint32_t *slot_well,
+                            uint32_t n_slots, int n_tiles, int len, uint64_t *packed) {
+    if (all_bcl) launch_gather<W, true>(ctx, descs, slot_well, n_slots, n_tiles, len, packed);
+    else launch_gather<W, false>(ctx, descs, slot_well, n_slots, n_tiles, len, packed);
+}
+
+static void launch_gather_any(wd_ctx *ctx, int words, bool all_bcl, const TileDesc *descs, const uint32_t *slot_well,
+                              uint32_t n_slots, int n_tiles, int len, uint64_t *packed) {
+    switch (words) {
+        case 1: launch_gather_w<1>(ctx, all_bcl, descs, slot_well, n_slots, n_tiles, len, packed); break;
+        case 2: launch_gather_w<2>(ctx, all_bcl, descs, slot_well, n_slots, n_tiles, len, packed); break;
+        case 4: launch_gather_w<4>(ctx, all_bcl, descs, slot_well, n_slots, n_tiles, len, packed); break;
+        case 8: launch_gather_w<8>(ctx, all_bcl, descs, slot_well, n_slots, n_tiles, len, packed); break;
+        default: launch_gather_w<16>(ctx, all_bcl, descs, slot_well, n_slots, n_tiles, len, packed); break;
+    }
+}
+
+int get_seqs(wd_ctx *ctx, int slot, const int64_t *indices, uint32_t n_idx, const int32_t *order, int seq_len,
+             uint8_t *codes, uint8_t *pf) {
+    if (slot < 0 || (size_t)slot >= ctx->slots.size() || ctx->slots[slot].n == 0)
+        WD_FAIL(WD_E_ARG, "tile slot %d has not been begun", slot);
+    TileSlot &s = ctx->slots[slot];
+    if (n_idx == 0) return WD_OK;
+    // bcl_direct_reader.py:186-192
+    int64_t mx = indices[0], mn = indices[0];
+    for (uint32_t i = 1; i < n_idx; ++i) {
+        mx = indices[i] > mx ? indices[i] : mx;
+        mn = indices[i] < mn ? indices[i] : mn;
+    }
+    if (mx >= (int64_t)s.n)
+        WD_FAIL(WD_E_INDEX, "Requested cluster %lld is out of range.  Highest on this tile is %u.", (long long)mx, s.n - 1);
+    if (mn < 0) WD_FAIL(WD_E_INDEX, "Requested cluster %lld is a negative number.", (long long)mn);
+    cudaStream_t st = ctx->stream;
+    std::vector<uint32_t> wells(n_idx);
+    for (uint32_t i = 0; i < n_idx; ++i) wells[i] = (uint32_t)indices[i];
+    WD_TRY(ctx->gs_idx.reserve((size_t)n_idx * 4));
+    WD_CUDA(cudaMemcpyAsync(ctx->gs_idx.p, wells.data(), (size_t)n_idx * 4, cudaMemcpyHostToDevice, st));
+    if (!s.filter_set) WD_FAIL(WD_E_ARG, "tile slot %d has no filter loaded", slot);
+    if (seq_len == 0) {
+        // zero-length range: only the flags
+        WD_TRY(filter_rank(ctx, &slot, 1));
+        std::vector<uint8_t> f(s.n);
+        WD_CUDA(cudaMemcpyAsync(f.data(), s.filter.p, s.n, cudaMemcpyDeviceToHost, st));
+        WD_CUDA(cudaStreamSynchronize(st));
+        for (uint32_t i = 0; i < n_idx; ++i) pf[i] = f[wells[i]] & 1;
+        return WD_OK;
+    }
+    bool all_bcl, any_excl;
+    WD_TRY(prepare_order(ctx, slot, 1, order, seq_len, &all_bcl, &any_excl));
+    if (any_excl) WD_TRY(filter_rank(ctx, &slot, 1));
+    WD_TRY(upload_descs(ctx, slot, 1));
+    const int words = words_for(seq_len);
+    WD_TRY(ctx->gs_packed.reserve((size_t)n_idx * words * PACK_STRIDE * 8));
+    WD_TRY(ctx->gs_codes.reserve((size_t)n_idx * seq_len + n_idx));
+    launch_gather_any(ctx, words, all_bcl, ctx->descs.as<TileDesc>(), ctx->gs_idx.as<uint32_t>(), n_idx, 1, seq_len,
+                      ctx->gs_packed.as<uint64_t>());
+    uint8_t *d_codes = ctx->gs_codes.as<uint8_t>();
+    uint8_t *d_pf = d_codes + (size_t)n_idx * seq_len;
+    const unsigned blocks = (n_idx + 255) / 256;
+    switch (words) {
+        case 1: unpack_codes_kernel<1><<<blocks, 256, 0, st>>>(ctx->gs_packed.as<uint64_t>(), n_idx, seq_len, d_codes, d_pf); break;
+        case 2: unpack_codes_kernel<2><<<blocks, 256, 0, st>>>(ctx->gs_packed.as<uint64_t>(), n_idx, seq_len, d_codes, d_pf); break;
+        case 4: unpack_codes_kernel<4><<<blocks, 256, 0, st>>>(ctx->gs_packed.as<uint64_t>(), n_idx, seq_len, d_codes, d_pf); break;
+        case 8: unpack_codes_kernel<8><<<blocks, 256, 0, st>>>(ctx->gs_packed.as<uint64_t>(), n_idx, seq_len, d_codes, d_pf); break;
+        default: unpack_codes_kernel<16><<<blocks, 256, 0, st>>>(ctx->gs_packed.as<uint64_t>(), n_idx, seq_len, d_codes, d_pf); break;
+    }
+    ctx->launches++;
+    WD_CUDA(cudaGetLastError());
+    WD_CUDA(cudaMemcpyAsync(codes, d_codes, (size_t)n_idx * seq_len, cudaMemcpyDeviceToHost, st));
+    WD_CUDA(cudaMemcpyAsync(pf, d_pf, (size_t)n_idx, cudaMemcpyDeviceToHost, st));
+    WD_CUDA(cudaStreamSynchronize(st));
+    return WD_OK;
+}
+
+template <int W, int LMAX>
+static void launch_count(wd_ctx *ctx, const CountArgs &a, int n_tiles, int mode, bool all_bcl) {
+    dim3 grid((a.t + CNT_WARPS - 1) / CNT_WARPS, n_tiles);
+    if (mode == 1) {
+        compare_count_kernel<W, LMAX><<<grid, CNT_WARPS * 32, 0, ctx->stream>>>(a);
+    } else if (all_bcl) {
+        fused_count_kernel<W, LMAX, true><<<grid, CNT_WARPS * 32, 0, ctx->stream>>>(a);
+    } else {
+        fused_count_kernel<W, LMAX, false><<<grid, CNT_WARPS * 32, 0, ctx->stream>>>(a);
+    }
+    ctx->launches++;
+}
+
+template <int W>
+static void launch_count_w(wd_ctx *ctx, const CountArgs &a, int n_tiles, int mode, bool all_bcl) {
+    if (a.levels <= 5) launch_count<W, 5>(ctx, a, n_tiles, mode, all_bcl);
+    else launch_count<W, WD_MAX_LEVELS>(ctx, a, n_tiles, mode, all_bcl);
+}
+
+int count_async(wd_ctx *ctx, int first_slot, int n_tiles, const int32_t *order, int seq_len, int e, int hamming,
+                int mode, int want_per_target) {
+    TargetList &tl = ctx->targets;
+    if (tl.t == 0) WD_FAIL(WD_E_ARG, "wd_count: no target list loaded");
+    if (mode != 0 && mode != 1) WD_FAIL(WD_E_ARG, "wd_count: mode must be 0 (fused) or 1 (two-pass)");
+    if (n_tiles > 65535) WD_FAIL(WD_E_ARG, "wd_count: at most 65535 tiles per call");
+    bool all_bcl, any_excl;
+    WD_TRY(prepare_order(ctx, first_slot, n_tiles, order, seq_len, &all_bcl, &any_excl));
+    for (int k = 0; k < n_tiles; ++k) {
+        const TileSlot &s = ctx->slots[first_slot + k];
+        if (tl.max_well >= s.n)
+            WD_FAIL(WD_E_INDEX, "Requested cluster %u is out of range.  Highest on this tile is %u.", tl.max_well, s.n - 1);
+    }
+    if (any_excl) {
+        for (int k = 0; k < n_tiles; ++k) {
+            const int id = first_slot + k;
+            WD_TRY(filter_rank(ctx, &id, 1));
+        }
+    }
+    WD_TRY(upload_descs(ctx, first_slot, n_tiles));
+    cudaStream_t st = ctx->stream;
+    const int L = tl.levels;
+    const size_t width = 1 + 5 * (size_t)L;
+    WD_TRY(ctx->counters.reserve((size_t)n_tiles * width * 8));
+    WD_CUDA(cudaMemsetAsync(ctx->counters.p, 0, (size_t)n_tiles * width * 8, st));
+    if (want_per_target) WD_TRY(ctx->per_target.reserve((size_t)n_tiles * tl.t * (1 + 2 * L) * 4));
+    const int words = words_for(seq_len);
+
+    CountArgs a;
+    a.descs = ctx->descs.as<TileDesc>();
+    a.tgt_off = tl.tgt_off.as<uint32_t>();
+    a.slot_well = tl.slot_well.as<uint32_t>();
+    a.slot_csr = tl.slot_csr.as<uint32_t>();
+    a.level_len = tl.level_len.as<uint32_t>();
+    a.slot_level = tl.slot_level.as<uint8_t>();
+    a.g_off = ctx->order_dev.as<unsigned long long>();
+    a.g_kind = ctx->order_dev.as<uint8_t>() + (size_t)MAX_ORDER * 8;
+    a.packed = nullptr;
+    a.per_target = want_per_target ? ctx->per_target.as<int32_t>() : nullptr;
+    a.counters = ctx->counters.as<unsigned long long>();
+    a.dup_rows = nullptr;
+    a.dup_count = nullptr;
+    a.dup_cap = 0;
+    a.t = tl.t;
+    a.n_slots = tl.n_slots;
+    a.levels = L;
+    a.len = seq_len;
+    a.e = e;
+    a.hamming = hamming;
+
+    if (mode == 1) {
+        WD_TRY(ctx->packed.reserve((size_t)n_tiles * tl.n_slots * words * PACK_STRIDE * 8));
+        launch_gather_any(ctx, words, all_bcl, a.descs, a.slot_well, tl.n_slots, n_tiles, seq_len,
+                          ctx->packed.as<uint64_t>());
+        a.packed = ctx->packed.as<uint64_t>();
+        // duplicate-pair log: room for every ring slot of 1/8 of the targets, at least 64k rows
+        size_t cap = (size_t)n_tiles * tl.n_slots / 8 + 65536;
+        WD_TRY(ctx->dup_rows.reserve(cap * 16));
+        WD_TRY(ctx->dup_count.reserve(8));
+        WD_CUDA(cudaMemsetAsync(ctx->dup_count.p, 0, 8, st));
+        ctx->dup_cap = cap;
+        a.dup_rows = ctx->dup_rows.as<int32_t>();
+        a.dup_count = ctx->dup_count.as<unsigned long long>();
+        a.dup_cap = cap;
+    } else {
+        ctx->dup_cap = 0;
+    }
+    switch (words) {
+        case 1: launch_count_w<1>(ctx, a, n_tiles, mode, all_bcl); break;
+        case 2: launch_count_w<2>(ctx, a, n_tiles, mode, all_bcl); break;
+        case 4: launch_count_w<4>(ctx, a, n_tiles, mode, all_bcl); break;
+        case 8: launch_count_w<8>(ctx, a, n_tiles, mode, all_bcl); break;
+        default: launch_count_w<16>(ctx, a, n_tiles, mode, all_bcl); break;
+    }
+    WD_CUDA(cudaGetLastError());
+    ctx->last_tiles = n_tiles;
+    ctx->last_levels = L;
+    ctx->last_t = tl.t;
+    ctx->last_first_slot = first_slot;
+    ctx->last_per_target = want_per_target != 0;
+    return WD_OK;
+}
+
+int publish_counters(wd_ctx *ctx, const int32_t *tile_row, const int32_t *lane_row, int n_tiles, int n_rows_total) {
+    if (n_tiles != ctx->last_tiles) WD_FAIL(WD_E_ARG, "wd_publish_counters: last wd_count covered %d tiles, not %d", ctx->last_tiles, n_tiles);
+    const int width = 1 + 5 * ctx->last_levels;
+    for (int i = 0; i < n_tiles; ++i)
+        if (tile_row[i] >= n_rows_total || lane_row[i] >= n_rows_total)
+            WD_FAIL(WD_E_ARG, "wd_publish_counters: row index out of range");
+    cudaStream_t st = ctx->stream;
+    const size_t n = (size_t)n_rows_total * width;
+    WD_TRY(ctx->publish.reserve(n * 8 + (size_t)n_tiles * 8));
+    int32_t *rows = reinterpret_cast<int32_t *>(ctx->publish.as<unsigned long long>() + n);
+    WD_CUDA(cudaMemsetAsync(ctx->publish.p, 0, n * 8, st));
+    WD_CUDA(cudaMemcpyAsync(rows, tile_row, (size_t)n_tiles * 4, cudaMemcpyHostToDevice, st));
+    WD_CUDA(cudaMemcpyAsync(rows + n_tiles, lane_row, (size_t)n_tiles * 4, cudaMemcpyHostToDevice, st));
+    const int total = n_tiles * width;
+    publish_kernel<<<(total + 255) / 256, 256, 0, st>>>(ctx->counters.as<unsigned long long>(), rows, rows + n_tiles,
+                                                         n_tiles, width, ctx->publish.as<unsigned long long>());
+    ctx->launches++;
+    WD_CUDA(cudaGetLastError());
+    ctx->publish_n = n;
+    return WD_OK;
+}
+
+int count_exhaustive(wd_ctx *, int, const int32_t *, int, int, uint32_t, uint32_t, int, int, int64_t *) {
+    WD_FAIL(WD_E_ARG, "wd_count_exhaustive: not built yet");
+}
+
+}  // namespace wd

@@ -114,7 +114,9 @@ def make_tile(rng: np.random.Generator, n_wells: int, n_cycles: int, row_len: in
     shifted by one base instead (Levenshtein 2, Hamming large), so the default
     (Levenshtein) and ``--hamming`` modes give different counts.
     """
-    base = rng.integers(0, 4, size=(n_cycles, n_wells), dtype=np.uint8)
+    base = np.empty((n_cycles, n_wells), dtype=np.uint8)
+    for c in range(n_cycles):
+        base[c] = rng.integers(0, 4, size=n_wells, dtype=np.uint8)
     n_dup = int(n_wells * dup_rate)
     if n_dup:
         offs = lattice_offsets(row_len)
@@ -135,11 +137,12 @@ def make_tile(rng: np.random.Generator, n_wells: int, n_cycles: int, row_len: in
         d1, s1 = dst[shifted], src[shifted]
         if n_cycles > 1 and d1.size:
             base[1:, d1] = base[:-1, s1]
-    qual = QUALS[rng.integers(0, QUALS.size, size=(n_cycles, n_wells))]
-    planes = (base | (qual << 2)).astype(np.uint8)
-    del base, qual
-    if nocall_rate > 0:
-        planes[rng.random((n_cycles, n_wells), dtype=np.float32) < nocall_rate] = 0
+    planes = base            # finished in place, one cycle at a time (bounded memory at full tile size)
+    for c in range(n_cycles):
+        qual = QUALS[rng.integers(0, QUALS.size, size=n_wells, dtype=np.uint8)]
+        planes[c] |= qual << 2
+        if nocall_rate > 0:
+            planes[c][rng.random(n_wells, dtype=np.float32) < nocall_rate] = 0
     filt = (rng.random(n_wells) < pf_rate).astype(np.uint8)
     # real filter files sometimes carry other bits; bit0 alone decides PF
     filt |= (rng.integers(0, 2, size=n_wells, dtype=np.uint8) << 1)
