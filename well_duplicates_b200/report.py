@@ -42,17 +42,22 @@ def dupl_from_per_target(per_target, levels):
     return out
 
 
-def format_report(lane, sample_size, tiles, counters, levels, verbose=False):
-    """Text for tiles (names, already in print order) with counter rows."""
-    out = []
+def write_report(stream, lane, sample_size, tiles, counters, levels, verbose=False):
+    """Writes the report for tiles (names, already in print order) with counter
+    rows.  Lines go out as they are produced, so a lane without any hit prints
+    its per-tile lines and then raises ZeroDivisionError exactly where the
+    reference does (count_well_duplicates.py:115-117)."""
+    def emit(line):
+        stream.write(line + "\n")
+
     tot = [0] * (1 + 5 * levels)
     for tile, row in zip(tiles, counters):
         row = [int(v) for v in row]
         if verbose:
-            out.append("Lane: %s\tTile: %s\tTargets: %i/%i" % (lane, tile, row[0], sample_size))
+            emit("Lane: %s\tTile: %s\tTargets: %i/%i" % (lane, tile, row[0], sample_size))
             for lev in range(levels):
                 w, d, h, o, i = row[1 + 5 * lev: 6 + 5 * lev]
-                out.append("Level: %i\tWells: %i\tDups: %i\tHit: %i\tAccO: %i\tAccI: %i" % (lev + 1, w, d, h, o, i))
+                emit("Level: %i\tWells: %i\tDups: %i\tHit: %i\tAccO: %i\tAccI: %i" % (lev + 1, w, d, h, o, i))
         tot = [a + b for a, b in zip(tot, row[: len(tot)])]
     targets = tot[0]
     if levels:
@@ -62,17 +67,23 @@ def format_report(lane, sample_size, tiles, counters, levels, verbose=False):
         peds2 = hits_any * (1 - hits_any / (2 * dups_all)) / targets
     else:
         hits_any = peds = peds2 = 0
-    out.append("LaneSummary: %s\tTiles: %i\tTargets: %i/%i" % (lane, len(tiles), targets, sample_size * len(tiles)))
+    emit("LaneSummary: %s\tTiles: %i\tTargets: %i/%i" % (lane, len(tiles), targets, sample_size * len(tiles)))
     for lev in range(levels):
         w, d, h, o, i = tot[1 + 5 * lev: 6 + 5 * lev]
-        out.append("Level: %i\tWells: %i\tDups: %i (%.5f)\tHit: %i (%.5f)\tAccO: %i (%.5f)\tAccI: %i (%.5f)" % (
+        emit("Level: %i\tWells: %i\tDups: %i (%.5f)\tHit: %i (%.5f)\tAccO: %i (%.5f)\tAccI: %i (%.5f)" % (
             lev + 1, w, d, d / w, h, h / targets, o, o / targets, i, i / targets))
     raw = hits_any / targets if hits_any else 0.0
-    out.append("")
-    out.append("Overall duplication (Acc/Targets): {:.2%}".format(raw))
-    out.append("Picard-equivalent duplication v1:  {:.2%}".format(peds))
-    out.append("Picard-equivalent duplication v2:  {:.2%}".format(peds2))
-    return "".join(line + "\n" for line in out)
+    emit("")
+    emit("Overall duplication (Acc/Targets): {:.2%}".format(raw))
+    emit("Picard-equivalent duplication v1:  {:.2%}".format(peds))
+    emit("Picard-equivalent duplication v2:  {:.2%}".format(peds2))
+
+
+def format_report(lane, sample_size, tiles, counters, levels, verbose=False):
+    import io
+    buf = io.StringIO()
+    write_report(buf, lane, sample_size, tiles, counters, levels, verbose)
+    return buf.getvalue()
 
 
 def output_writer(lane, sample_size, lane_dupl, levels=0, verbose=False):
@@ -86,4 +97,4 @@ def output_writer(lane, sample_size, lane_dupl, levels=0, verbose=False):
                 break
     tiles = sorted(lane_dupl.keys())
     rows = [counters_from_dupl(lane_dupl[t], levels) for t in tiles]
-    sys.stdout.write(format_report(lane, sample_size, tiles, rows, levels, verbose))
+    write_report(sys.stdout, lane, sample_size, tiles, rows, levels, verbose)
