@@ -74,6 +74,10 @@ WD_API int wd_sync(wd_ctx *ctx);
 /* Pinned host memory, so that wd_tile_put_* / wd_locs_load copy by DMA without staging. */
 WD_API int wd_host_alloc(size_t bytes, void **out);
 WD_API int wd_host_free(void *p);
+/* DRAM->L2 fill granularity hint for the current device (32, 64 or 128 bytes;
+ * cudaLimitMaxL2FetchGranularity).  The scattered plane gathers use a few bytes
+ * per 32-byte sector, so wd_create() asks for 32; *previous receives the old value. */
+WD_API int wd_set_l2_fetch_granularity(wd_ctx *ctx, int bytes, int *previous);
 /* Number of kernel launches issued by this context so far (bench.py gpu_launches). */
 WD_API int wd_launch_count(wd_ctx *ctx, uint64_t *out);
 

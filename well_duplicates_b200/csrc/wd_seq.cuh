@@ -107,38 +107,64 @@ WD_HD uint64_t shifted_word(const uint64_t *p, int w, int d) {
 // of b that the script matches exactly is matched to a[j+d] for some
 // |d| <= k; every other symbol of b costs at least one edit.  Hence the
 // number of positions j with a[j+d] != b[j] for ALL |d| <= k is <= e whenever
-// Lev(a,b) <= e.  Returns true when that bound proves Lev(a,b) > e.
+// Lev(a,b) <= e -- and that stays true if only the positions j < prefix are
+// counted, which is what lets the gather stop reading planes for a well as
+// soon as its first symbols rule it out.  a is known over [0, len); b over
+// [0, prefix).  Returns the count.
+template <int W>
+WD_HD int shd_bad_count(const PSeq<W> &a, const PSeq<W> &b, int len, int prefix, int k) {
+    int bad = 0;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        const uint64_t lm = len_mask(prefix, w);
+        if (lm != 0ull) {
+            uint64_t all = lm;
+            for (int d = -k; d <= k; ++d) {
+                uint64_t mm = (shifted_word<W>(a.lo, w, d) ^ b.lo[w]) |
+                              (shifted_word<W>(a.hi, w, d) ^ b.hi[w]) |
+                              (shifted_word<W>(a.nn, w, d) ^ b.nn[w]);
+                // positions whose partner j+d falls outside [0, len) cannot match
+                if (d > 0) {
+                    const int cut = len - d - 64 * w;   // first invalid bit in this word
+                    if (cut <= 0) mm = ~0ull;
+                    else if (cut < 64) mm |= ~((1ull << cut) - 1ull);
+                } else if (d < 0) {
+                    const int cut = -d - 64 * w;        // bits [0, cut) invalid
+                    if (cut >= 64) mm = ~0ull;
+                    else if (cut > 0) mm |= (1ull << cut) - 1ull;
+                }
+                all &= mm;
+            }
+            bad += popc64(all);
+        }
+    }
+    return bad;
+}
+
+// true when the bound proves Lev(a,b) > e
 template <int W>
 WD_HD bool shd_rejects(const PSeq<W> &a, const PSeq<W> &b, int len, int e) {
     const int k = e >> 1;
     if (k >= 64) return false;
-    int bad = 0;
+    return shd_bad_count<W>(a, b, len, len, k) > e;
+}
+
+// true when the first `prefix` symbols of b (the rest of b still unknown,
+// stored as zero bits) already prove dist(a, b) > e under the chosen metric.
+template <int W>
+WD_HD bool prefix_rejects(const PSeq<W> &a, const PSeq<W> &b, int len, int prefix, int e, bool use_hamming) {
+    if (e < 0) return true;
+    if (e >= len) return false;
+    if (use_hamming || e < 2) {                // Lev <= 1 <=> Ham <= 1
+        int d = 0;
 #pragma unroll
-    for (int w = 0; w < W; ++w) {
-        const uint64_t lm = len_mask(len, w);
-        if (lm == 0ull) break;
-        uint64_t all = lm;
-        for (int d = -k; d <= k; ++d) {
-            uint64_t mm = (shifted_word<W>(a.lo, w, d) ^ b.lo[w]) |
-                          (shifted_word<W>(a.hi, w, d) ^ b.hi[w]) |
-                          (shifted_word<W>(a.nn, w, d) ^ b.nn[w]);
-            // positions whose partner j+d falls outside [0, len) cannot match
-            if (d > 0) {
-                // j >= len - d
-                const int cut = len - d - 64 * w;   // first invalid bit in this word
-                if (cut <= 0) mm = ~0ull;
-                else if (cut < 64) mm |= ~((1ull << cut) - 1ull);
-            } else if (d < 0) {
-                // j < -d
-                const int cut = -d - 64 * w;        // bits [0, cut) invalid
-                if (cut >= 64) mm = ~0ull;
-                else if (cut > 0) mm |= (1ull << cut) - 1ull;
-            }
-            all &= mm;
-        }
-        bad += popc64(all);
+        for (int w = 0; w < W; ++w)
+            d += popc64(((a.lo[w] ^ b.lo[w]) | (a.hi[w] ^ b.hi[w]) | (a.nn[w] ^ b.nn[w])) & len_mask(prefix, w));
+        return d > e;
     }
-    return bad > e;
+    const int k = e >> 1;
+    if (k >= 64) return false;
+    return shd_bad_count<W>(a, b, len, prefix, k) > e;
 }
 
 // Exact unit-cost edit distance between two equal-length packed strings

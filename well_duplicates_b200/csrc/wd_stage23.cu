@@ -116,61 +116,63 @@ int filter_offsets(wd_ctx *ctx, int slot, int32_t *offsets, uint32_t *passing) {
 // ============================================================================
 // s_off[p]  = byte offset of the plane that supplies sequence position p
 // s_kind[p] = WD_PLANE_* of that plane (same for every tile of a launch)
+// one base call -> raw code: 0 = no-call, otherwise base = code & 3
+template <bool ALL_BCL>
+__device__ __forceinline__ uint32_t load_call(const TileDesc &d, uint32_t well, int rank, unsigned long long off,
+                                              int kind) {
+    if (ALL_BCL || kind == WD_PLANE_BCL) return __ldg(d.planes + off + well);
+    const int wi = kind == WD_PLANE_CBCL_EXCL ? rank : (int)well;
+    if (wi < 0) return 0u;                        // not PF: the block has no entry for it -> N
+    const uint32_t byte = __ldg(d.planes + off + ((uint32_t)wi >> 1));
+    return (wi & 1) ? (byte >> 4) : (byte & 15u);
+}
+
+// eight consecutive sequence positions p .. p+7 (those >= len contribute
+// nothing) -> 8-bit groups of the three planes.  The eight loads are issued
+// before any is consumed (memory-level parallelism).
+template <bool ALL_BCL>
+__device__ __forceinline__ void decode8(const TileDesc &d, uint32_t well, int rank, const unsigned long long *s_off,
+                                        const uint8_t *s_kind, int p, int len, uint32_t &glo, uint32_t &ghi,
+                                        uint32_t &gnn) {
+    uint32_t code[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        code[j] = 4u;                            // beyond the sequence: no bit in any plane
+        if (p + j < len) code[j] = load_call<ALL_BCL>(d, well, rank, s_off[p + j], ALL_BCL ? 0 : s_kind[p + j]);
+    }
+    glo = ghi = gnn = 0;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const uint32_t b = code[j];
+        glo |= (b & 1u) << j;
+        ghi |= ((b >> 1) & 1u) << j;
+        gnn |= (b == 0u ? 1u : 0u) << j;
+    }
+}
+
+template <int W>
+__device__ __forceinline__ void pseq_or8(PSeq<W> &q, int p, uint32_t glo, uint32_t ghi, uint32_t gnn) {
+    const int w = p >> 6, sh = p & 63;           // p is a multiple of 8: a group never straddles words
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        if (i == w) {
+            q.lo[i] |= (uint64_t)glo << sh;
+            q.hi[i] |= (uint64_t)ghi << sh;
+            q.nn[i] |= (uint64_t)gnn << sh;
+        }
+    }
+}
+
 template <int W, bool ALL_BCL>
 __device__ __forceinline__ void decode_well(const TileDesc &d, uint32_t well, const unsigned long long *s_off,
                                             const uint8_t *s_kind, int len, PSeq<W> &out) {
     int rank = 0;
     if (!ALL_BCL && (d.flags & 1u)) rank = pf_rank(d, well);
-    const uint8_t *base = d.planes;
-#pragma unroll
-    for (int w = 0; w < W; ++w) {
-        uint64_t lo = 0, hi = 0, nn = 0;
-        const int p0 = 64 * w;
-        const int cnt = min(64, len - p0);
-        for (int i0 = 0; i0 < cnt; i0 += 8) {
-            uint32_t code[8];
-            // issue the eight independent loads first (memory-level parallelism) ...
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const int p = p0 + i0 + j;
-                code[j] = 4u;                    // beyond the sequence: contributes no bit to any plane
-                if (i0 + j < cnt) {
-                    if (ALL_BCL) {
-                        code[j] = __ldg(base + s_off[p] + well);
-                    } else {
-                        const int kind = s_kind[p];
-                        if (kind == WD_PLANE_BCL) {
-                            code[j] = __ldg(base + s_off[p] + well);
-                        } else {
-                            const int wi = kind == WD_PLANE_CBCL_EXCL ? rank : (int)well;
-                            uint32_t nib = 0;
-                            if (wi >= 0) {
-                                const uint32_t byte = __ldg(base + s_off[p] + ((uint32_t)wi >> 1));
-                                nib = (wi & 1) ? (byte >> 4) : (byte & 15u);
-                            }
-                            code[j] = nib;       // nibble 0 -> N, like byte 0
-                        }
-                    }
-                }
-            }
-            // ... then fold them into 8-bit groups of the three planes:
-            // base = code & 3; code 0 (no-call) sets the N plane and no base bit
-            uint32_t glo = 0, ghi = 0, gnn = 0;
-#pragma unroll
-            for (int j = 0; j < 8; ++j) {
-                const uint32_t b = code[j];
-                glo |= (b & 1u) << j;
-                ghi |= ((b >> 1) & 1u) << j;
-                gnn |= (b == 0u ? 1u : 0u) << j;
-            }
-            lo |= (uint64_t)glo << i0;
-            hi |= (uint64_t)ghi << i0;
-            nn |= (uint64_t)gnn << i0;
-        }
-        // canonical form: N positions carry no base bits (true by construction: code 0)
-        out.lo[w] = lo;
-        out.hi[w] = hi;
-        out.nn[w] = nn;
+    pseq_clear(out);
+    for (int p = 0; p < len; p += 8) {
+        uint32_t glo, ghi, gnn;
+        decode8<ALL_BCL>(d, well, rank, s_off, s_kind, p, len, glo, ghi, gnn);
+        pseq_or8<W>(out, p, glo, ghi, gnn);
     }
 }
 
@@ -365,8 +367,15 @@ compare_count_kernel(CountArgs a) {
 
 // fused flavour (production): the warp gathers and decodes its target's wells
 // straight from the planes, compares in registers and never writes the packed
-// words.  Targets whose centre fails the filter are skipped before any plane
-// byte is read.
+// words.
+//  * targets whose centre fails the filter are skipped before any plane byte
+//    is read;
+//  * the centre is decoded by the whole warp (lane = cycle, three ballots turn
+//    32 calls into one word of each bit-plane);
+//  * ring wells are decoded 8 cycles at a time, one well per lane, and a well
+//    stops being read as soon as its prefix proves dist > e (prefix_rejects):
+//    unrelated reads drop out after 16-24 of 50 cycles, so the later planes are
+//    touched only in the centre's row and around real duplicates.
 template <int W, int LMAX, bool ALL_BCL>
 __global__ void __launch_bounds__(CNT_WARPS * 32)
 fused_count_kernel(CountArgs a) {
@@ -383,31 +392,58 @@ fused_count_kernel(CountArgs a) {
         const uint32_t s0 = __ldg(a.tgt_off + t), s1 = __ldg(a.tgt_off + t + 1);
         const uint32_t centre = __ldg(a.slot_well + s0);
         const bool valid = (__ldg(d.filter + centre) & 1u) != 0;
+        const bool ham = a.hamming != 0;
         uint32_t dups[LMAX];
 #pragma unroll
         for (int l = 0; l < LMAX; ++l) dups[l] = 0;
         if (valid) {
+            // ---- centre: lane = cycle ------------------------------------------------
             PSeq<W> c;
-            // first chunk: lane 0 decodes the centre, lanes 1..31 the first ring slots
-            for (uint32_t base = s0; base < s1; base += 32) {
+            {
+                int crank = 0;
+                if (!ALL_BCL && (d.flags & 1u)) crank = pf_rank(d, centre);
+#pragma unroll
+                for (int w = 0; w < W; ++w) {
+                    uint32_t lo2[2], hi2[2], nn2[2];
+#pragma unroll
+                    for (int h = 0; h < 2; ++h) {
+                        const int p = 64 * w + 32 * h + lane;
+                        uint32_t code = 4u;
+                        if (p < a.len) code = load_call<ALL_BCL>(d, centre, crank, s_off[p], ALL_BCL ? 0 : s_kind[p]);
+                        lo2[h] = __ballot_sync(0xffffffffu, code & 1u);
+                        hi2[h] = __ballot_sync(0xffffffffu, code & 2u);
+                        nn2[h] = __ballot_sync(0xffffffffu, code == 0u);
+                    }
+                    c.lo[w] = (uint64_t)lo2[0] | ((uint64_t)lo2[1] << 32);
+                    c.hi[w] = (uint64_t)hi2[0] | ((uint64_t)hi2[1] << 32);
+                    c.nn[w] = (uint64_t)nn2[0] | ((uint64_t)nn2[1] << 32);
+                }
+            }
+            // ---- ring wells: lane = well, 8 cycles per round, early exit -----------------
+            for (uint32_t base = s0 + 1; base < s1; base += 32) {
                 const uint32_t s = base + lane;
+                const bool mine = s < s1;
+                uint32_t well = 0;
+                int lvl = 0, rank = 0;
+                if (mine) {
+                    well = __ldg(a.slot_well + s);
+                    lvl = __ldg(a.slot_level + s);
+                    if (!ALL_BCL && (d.flags & 1u)) rank = pf_rank(d, well);
+                }
                 PSeq<W> b;
                 pseq_clear(b);
-                int lvl = 0;
-                if (s < s1) {
-                    decode_well<W, ALL_BCL>(d, __ldg(a.slot_well + s), s_off, s_kind, a.len, b);
-                    lvl = __ldg(a.slot_level + s);
-                }
-                if (base == s0) {
-#pragma unroll
-                    for (int w = 0; w < W; ++w) {
-                        c.lo[w] = __shfl_sync(0xffffffffu, b.lo[w], 0);
-                        c.hi[w] = __shfl_sync(0xffffffffu, b.hi[w], 0);
-                        c.nn[w] = __shfl_sync(0xffffffffu, b.nn[w], 0);
+                bool alive = mine;
+                for (int p = 0; p < a.len; p += 8) {
+                    if (!__any_sync(0xffffffffu, alive)) break;
+                    if (alive) {
+                        uint32_t glo, ghi, gnn;
+                        decode8<ALL_BCL>(d, well, rank, s_off, s_kind, p, a.len, glo, ghi, gnn);
+                        pseq_or8<W>(b, p, glo, ghi, gnn);
+                        const int known = min(p + 8, a.len);
+                        if (known < a.len && prefix_rejects<W>(c, b, a.len, known, a.e, ham)) alive = false;
                     }
                 }
-                bool dup = false;
-                if (s < s1 && lvl > 0) dup = is_duplicate<W>(c, b, a.len, a.e, a.hamming != 0);
+                const bool dup = alive && is_duplicate<W>(c, b, a.len, a.e, ham);
 #pragma unroll
                 for (int l = 0; l < LMAX; ++l)
                     if (l < a.levels) dups[l] += __popc(__ballot_sync(0xffffffffu, dup && lvl == l + 1));

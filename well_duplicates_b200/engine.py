@@ -61,6 +61,12 @@ class Engine:
     def sync(self):
         _lib.check(self._lib.wd_sync(self._h))
 
+    def set_l2_fetch_granularity(self, nbytes):
+        """-> previous value of cudaLimitMaxL2FetchGranularity."""
+        prev = C.c_int32()
+        _lib.check(self._lib.wd_set_l2_fetch_granularity(self._h, int(nbytes), C.byref(prev)))
+        return prev.value
+
     def launch_count(self):
         n = C.c_uint64()
         _lib.check(self._lib.wd_launch_count(self._h, C.byref(n)))
