@@ -16,6 +16,9 @@
 #include "wd_scan.cuh"
 #include "wd_seq.cuh"
 
+#include <cstdio>
+#include <cstdlib>
+
 namespace wd {
 
 constexpr int PACK_STRIDE = 4;   // u64 per 64-symbol word group in HBM: lo, hi, nn, meta (32 B)
@@ -127,22 +130,22 @@ __device__ __forceinline__ uint32_t load_call(const TileDesc &d, uint32_t well, 
     return (wi & 1) ? (byte >> 4) : (byte & 15u);
 }
 
-// eight consecutive sequence positions p .. p+7 (those >= len contribute
-// nothing) -> 8-bit groups of the three planes.  The eight loads are issued
-// before any is consumed (memory-level parallelism).
-template <bool ALL_BCL>
-__device__ __forceinline__ void decode8(const TileDesc &d, uint32_t well, int rank, const unsigned long long *s_off,
-                                        const uint8_t *s_kind, int p, int len, uint32_t &glo, uint32_t &ghi,
-                                        uint32_t &gnn) {
-    uint32_t code[8];
+// N (8 or 16) consecutive sequence positions p .. p+N-1 (those >= len
+// contribute nothing) -> N-bit groups of the three planes.  All N loads are
+// issued before any is consumed (memory-level parallelism).
+template <bool ALL_BCL, int N>
+__device__ __forceinline__ void decode_n(const TileDesc &d, uint32_t well, int rank, const unsigned long long *s_off,
+                                         const uint8_t *s_kind, int p, int len, uint32_t &glo, uint32_t &ghi,
+                                         uint32_t &gnn) {
+    uint32_t code[N];
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < N; ++j) {
         code[j] = 4u;                            // beyond the sequence: no bit in any plane
         if (p + j < len) code[j] = load_call<ALL_BCL>(d, well, rank, s_off[p + j], ALL_BCL ? 0 : s_kind[p + j]);
     }
     glo = ghi = gnn = 0;
 #pragma unroll
-    for (int j = 0; j < 8; ++j) {
+    for (int j = 0; j < N; ++j) {
         const uint32_t b = code[j];
         glo |= (b & 1u) << j;
         ghi |= ((b >> 1) & 1u) << j;
@@ -151,8 +154,8 @@ __device__ __forceinline__ void decode8(const TileDesc &d, uint32_t well, int ra
 }
 
 template <int W>
-__device__ __forceinline__ void pseq_or8(PSeq<W> &q, int p, uint32_t glo, uint32_t ghi, uint32_t gnn) {
-    const int w = p >> 6, sh = p & 63;           // p is a multiple of 8: a group never straddles words
+__device__ __forceinline__ void pseq_or_group(PSeq<W> &q, int p, uint32_t glo, uint32_t ghi, uint32_t gnn) {
+    const int w = p >> 6, sh = p & 63;           // groups start at multiples of their size: none straddles a word
 #pragma unroll
     for (int i = 0; i < W; ++i) {
         if (i == w) {
@@ -171,8 +174,8 @@ __device__ __forceinline__ void decode_well(const TileDesc &d, uint32_t well, co
     pseq_clear(out);
     for (int p = 0; p < len; p += 8) {
         uint32_t glo, ghi, gnn;
-        decode8<ALL_BCL>(d, well, rank, s_off, s_kind, p, len, glo, ghi, gnn);
-        pseq_or8<W>(out, p, glo, ghi, gnn);
+        decode_n<ALL_BCL, 8>(d, well, rank, s_off, s_kind, p, len, glo, ghi, gnn);
+        pseq_or_group<W>(out, p, glo, ghi, gnn);
     }
 }
 
@@ -260,6 +263,7 @@ struct CountArgs {
     unsigned long long dup_cap;
     uint32_t t, n_slots;
     int levels, len, e, hamming;
+    int step0, step1;                // fused kernel: cycles per round (first, later); 4, 8 or 16
 };
 
 // Per-warp tallies -> per_target row and the CTA's shared counters.
@@ -376,23 +380,35 @@ compare_count_kernel(CountArgs a) {
 //    stops being read as soon as its prefix proves dist > e (prefix_rejects):
 //    unrelated reads drop out after 16-24 of 50 cycles, so the later planes are
 //    touched only in the centre's row and around real duplicates.
+constexpr int FUSED_TPB = 64;    // targets per CTA; its 8 warps pull them from a shared counter
+
 template <int W, int LMAX, bool ALL_BCL>
 __global__ void __launch_bounds__(CNT_WARPS * 32)
 fused_count_kernel(CountArgs a) {
     __shared__ unsigned long long s_off[MAX_ORDER];
     __shared__ uint8_t s_kind[MAX_ORDER];
     __shared__ uint32_t s_cnt[1 + 5 * LMAX];
+    __shared__ uint32_t s_next;
     for (int i = threadIdx.x; i < 1 + 5 * LMAX; i += blockDim.x) s_cnt[i] = 0;
+    if (threadIdx.x == 0) s_next = 0;
     load_order(a.g_off, a.g_kind, a.len, s_off, s_kind);
     const int lane = threadIdx.x & 31;
     const uint32_t tile = blockIdx.y;
-    const uint32_t t = blockIdx.x * CNT_WARPS + (threadIdx.x >> 5);
-    if (t < a.t) {
-        const TileDesc d = a.descs[tile];
+    const TileDesc d = a.descs[tile];
+    const bool ham = a.hamming != 0;
+    const uint32_t t_begin = blockIdx.x * FUSED_TPB;
+    const uint32_t t_end = min(t_begin + FUSED_TPB, a.t);
+    // Targets differ a lot in cost (a failed centre costs one byte, a real
+    // duplicate keeps its warp reading to the last cycle), so warps take the
+    // next target when they are done instead of owning a fixed one.
+    for (;;) {
+        uint32_t t = 0;
+        if (lane == 0) t = t_begin + atomicAdd(&s_next, 1u);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= t_end) break;
         const uint32_t s0 = __ldg(a.tgt_off + t), s1 = __ldg(a.tgt_off + t + 1);
         const uint32_t centre = __ldg(a.slot_well + s0);
         const bool valid = (__ldg(d.filter + centre) & 1u) != 0;
-        const bool ham = a.hamming != 0;
         uint32_t dups[LMAX];
 #pragma unroll
         for (int l = 0; l < LMAX; ++l) dups[l] = 0;
@@ -419,7 +435,7 @@ fused_count_kernel(CountArgs a) {
                     c.nn[w] = (uint64_t)nn2[0] | ((uint64_t)nn2[1] << 32);
                 }
             }
-            // ---- ring wells: lane = well, 8 cycles per round, early exit -----------------
+            // ---- ring wells: lane = well; 16 cycles, then 8 at a time with early exit ------
             for (uint32_t base = s0 + 1; base < s1; base += 32) {
                 const uint32_t s = base + lane;
                 const bool mine = s < s1;
@@ -433,15 +449,23 @@ fused_count_kernel(CountArgs a) {
                 PSeq<W> b;
                 pseq_clear(b);
                 bool alive = mine;
-                for (int p = 0; p < a.len; p += 8) {
+                int p = 0;
+                while (p < a.len) {
                     if (!__any_sync(0xffffffffu, alive)) break;
+                    // cycles read before the next test: a.step0 for the first round (the
+                    // Levenshtein bound is too weak to drop anything after 8 symbols), a.step1 after
+                    const int step = p == 0 ? a.step0 : a.step1;
                     if (alive) {
                         uint32_t glo, ghi, gnn;
-                        decode8<ALL_BCL>(d, well, rank, s_off, s_kind, p, a.len, glo, ghi, gnn);
-                        pseq_or8<W>(b, p, glo, ghi, gnn);
-                        const int known = min(p + 8, a.len);
+                        if (step == 16) decode_n<ALL_BCL, 16>(d, well, rank, s_off, s_kind, p, a.len, glo, ghi, gnn);
+                        else if (step == 8) decode_n<ALL_BCL, 8>(d, well, rank, s_off, s_kind, p, a.len, glo, ghi, gnn);
+                        else if (step == 4) decode_n<ALL_BCL, 4>(d, well, rank, s_off, s_kind, p, a.len, glo, ghi, gnn);
+                        else decode_n<ALL_BCL, 2>(d, well, rank, s_off, s_kind, p, a.len, glo, ghi, gnn);
+                        pseq_or_group<W>(b, p, glo, ghi, gnn);
+                        const int known = min(p + step, a.len);
                         if (known < a.len && prefix_rejects<W>(c, b, a.len, known, a.e, ham)) alive = false;
                     }
+                    p += step;
                 }
                 const bool dup = alive && is_duplicate<W>(c, b, a.len, a.e, ham);
 #pragma unroll
@@ -624,12 +648,13 @@ int get_seqs(wd_ctx *ctx, int slot, const int64_t *indices, uint32_t n_idx, cons
 template <int W, int LMAX>
 static void launch_count(wd_ctx *ctx, const CountArgs &a, int n_tiles, int mode, bool all_bcl) {
     dim3 grid((a.t + CNT_WARPS - 1) / CNT_WARPS, n_tiles);
+    dim3 fgrid((a.t + FUSED_TPB - 1) / FUSED_TPB, n_tiles);
     if (mode == 1) {
         compare_count_kernel<W, LMAX><<<grid, CNT_WARPS * 32, 0, ctx->stream>>>(a);
     } else if (all_bcl) {
-        fused_count_kernel<W, LMAX, true><<<grid, CNT_WARPS * 32, 0, ctx->stream>>>(a);
+        fused_count_kernel<W, LMAX, true><<<fgrid, CNT_WARPS * 32, 0, ctx->stream>>>(a);
     } else {
-        fused_count_kernel<W, LMAX, false><<<grid, CNT_WARPS * 32, 0, ctx->stream>>>(a);
+        fused_count_kernel<W, LMAX, false><<<fgrid, CNT_WARPS * 32, 0, ctx->stream>>>(a);
     }
     ctx->launches++;
 }
@@ -689,6 +714,18 @@ int count_async(wd_ctx *ctx, int first_slot, int n_tiles, const int32_t *order, 
     a.len = seq_len;
     a.e = e;
     a.hamming = hamming;
+    // early-exit schedule of the fused kernel (cycles read per round: first, later), from the sweep
+    // in profiles/r01_early_exit_sweep.txt: short rounds win -- the traffic saved by dropping a well
+    // sooner outweighs the extra dependent round trips
+    a.step0 = (hamming || e < 2) ? 4 : 8;
+    a.step1 = 4;
+    if (const char *sch = getenv("WELLDUP_STEPS")) {
+        int s0 = 0, s1 = 0;
+        if (sscanf(sch, "%d,%d", &s0, &s1) == 2 && (s0 == 2 || s0 == 4 || s0 == 8 || s0 == 16) && (s1 == 2 || s1 == 4 || s1 == 8) && s0 % s1 == 0) {
+            a.step0 = s0;
+            a.step1 = s1;
+        }
+    }
 
     if (mode == 1) {
         WD_TRY(ctx->packed.reserve((size_t)n_tiles * tl.n_slots * words * PACK_STRIDE * 8));
