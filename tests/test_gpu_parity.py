@@ -376,3 +376,20 @@ def test_full_tile_monotone_in_e(eng, full_tile):
         if prev is not None:
             assert np.all(pt[0][:, 1::2] >= prev)
         prev = pt[0][:, 1::2]
+
+
+# ------------------------------------------------------------------ flowcell driver --
+@pytest.mark.parametrize("name", ["two_lanes", "lev_default", "cbcl_default", "summary"])
+def test_flowcell_driver_single_rank(name):
+    """One process, one GPU: the whole-run driver prints what the reference prints
+    lane after lane (the multi-rank exchange is covered on CPU by test_dist_gloo
+    and on 2 GPUs by tests/multi_gpu_check.sh)."""
+    from well_duplicates_b200 import flowcell
+    case = [c for c in MAN["count"] if c["name"] == name][0]
+    with open(os.path.join(GOLDEN, "count", name + ".stdout")) as fh:
+        want = fh.read()
+    argv = ["-f", os.path.join(GOLDEN, case["targets"]), "-r", os.path.join(GOLDEN, case["run"])] + case["args"] + ["-q"]
+    out = io.StringIO()
+    with contextlib.redirect_stdout(out):
+        flowcell.main(argv)
+    assert out.getvalue() == want

@@ -1,0 +1,155 @@
+"""Whole-flowcell driver: every lane of a run in one command, tiles sharded over
+the GPUs of one box.
+
+Replaces what the reference does with one process per lane plus a text
+concatenation (Snakefile.count_dups:143-160: rule count_well_dupl per lane, rule
+summarize_all_lanes = ``tail`` of the per-lane files): the (lane, tile) pairs are
+flattened in the reference's print order, rank r takes ordinals r, r+N, ...,
+each rank counts its tiles on its own GPU, and the integer counter rows
+``[Targets, (Wells, Dups, Hit, AccO, AccI) x levels]`` are combined by ONE
+all-reduce (int64, sum) -- NCCL over NVLink on the GPUs, gloo in the CPU tests.
+Every tile row is non-zero on exactly one rank, so the sum doubles as a gather
+for the per-tile printout, and the per-lane totals come out of the same call.
+Integer sums make the result independent of the rank count.
+
+    python -m torch.distributed.run --nproc-per-node 8 -m well_duplicates_b200.flowcell \\
+        -f targets.list -s 2224 -r RUN -l 5 --cycles 20-70 [-i 1,2,...] [-S]
+"""
+import os
+import sys
+from concurrent.futures import ThreadPoolExecutor
+
+import numpy as np
+
+from . import count_cli
+from .report import write_report
+
+
+def plan(n_lanes, tiles_per_lane, rank, world):
+    """Ordinals (lane-major, the reference's loop order) owned by ``rank``."""
+    total = n_lanes * tiles_per_lane
+    return np.arange(rank, total, world, dtype=np.int64)
+
+
+def rows_layout(n_lanes, tiles_per_lane):
+    """Row index of every tile and of every lane total in the exchange buffer."""
+    total = n_lanes * tiles_per_lane
+    return total, total + n_lanes
+
+
+def exchange_host(local_rows, mine, n_lanes, tiles_per_lane, width, dist=None):
+    """All-reduce of host rows (gloo / single process).  Returns the
+    [tiles + lanes, width] int64 array every rank ends up with."""
+    import torch
+    n_tile_rows, n_rows = rows_layout(n_lanes, tiles_per_lane)
+    buf = np.zeros((n_rows, width), dtype=np.int64)
+    if len(mine):
+        buf[mine] = local_rows
+        np.add.at(buf, n_tile_rows + mine // tiles_per_lane, local_rows)
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        t = torch.from_numpy(buf)
+        dist.all_reduce(t)
+    return buf
+
+
+class _DeviceInt64:
+    """Exposes a raw device pointer to torch through __cuda_array_interface__."""
+
+    def __init__(self, ptr, n):
+        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 2}
+
+
+def exchange_device(engine, mine, n_lanes, tiles_per_lane, device, dist=None):
+    """K7 (wd_publish_counters) + ncclAllReduce on the engine's device buffer,
+    for the counters of the engine's last count (its tiles = ``mine``)."""
+    import torch
+    n_tile_rows, n_rows = rows_layout(n_lanes, tiles_per_lane)
+    ptr, n = engine.publish_counters(mine.astype(np.int32), (n_tile_rows + mine // tiles_per_lane).astype(np.int32),
+                                     n_rows)
+    t = torch.as_tensor(_DeviceInt64(ptr, n), device=torch.device("cuda", device))
+    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
+        dist.all_reduce(t)
+    return t
+
+
+def print_reports(stream, lanes, tiles, buf, sample_size, levels, verbose):
+    """Per-lane reports, in lane order, from the exchanged rows."""
+    tpl = len(tiles)
+    order = np.argsort(np.array(tiles, dtype=object), kind="stable") if tiles else []
+    for li, lane in enumerate(lanes):
+        rows = buf[li * tpl:(li + 1) * tpl]
+        write_report(stream, lane, sample_size, [tiles[k] for k in order], [rows[k] for k in order], levels, verbose)
+
+
+def main(argv=None):
+    import torch
+    import torch.distributed as dist
+
+    from . import reader as bcl_direct_reader
+    from .engine import Engine
+    from .targets import load_targets
+
+    args = count_cli.parse_args(argv)
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    torch.cuda.set_device(local)
+    if world > 1 and not dist.is_initialized():
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    say = (lambda *a: None) if (args.quiet or rank != 0) else count_cli.log
+
+    lanes = args.lane.split(",") if args.lane else [str(x) for x in range(1, 9)]
+    tiles = count_cli.expected_tiles(args.stype, args.tile_id)
+    cycles = count_cli.parse_cycles(args)
+    wanted = [c for s, e in cycles for c in range(s, e)]
+    targets = load_targets(filename=args.coord_file, levels=args.level + 1, limit=args.sample_size)
+    eng = Engine(local)
+    stream = torch.cuda.Stream(device=local)
+    eng.set_stream(stream.cuda_stream)
+    centres, level_offsets, idx = targets.to_csr(args.level)
+    eng.load_targets(centres, level_offsets, idx, args.level)
+    rd = bcl_direct_reader.BCLReader(args.run, engine=eng)
+
+    mine = plan(len(lanes), len(tiles), rank, world)
+    width = 1 + 5 * args.level
+    rows = np.zeros((len(mine), width), dtype=np.int64)
+    budget = count_cli.HBM_BUDGET_BYTES
+    pool = ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1))
+    k = 0
+    with torch.cuda.stream(stream):
+        while k < len(mine):
+            n_batch = 0
+            first_n = None
+            plane_of = None
+            while k + n_batch < len(mine):
+                o = int(mine[k + n_batch])
+                lane, tile = lanes[o // len(tiles)], tiles[o % len(tiles)]
+                say("Reading tile %s in lane %s" % (tile, lane))
+                t = rd.get_tile(lane, tile)
+                if first_n is None:
+                    first_n = t.num_clusters
+                elif t.num_clusters != first_n:
+                    break
+                plane_of = t.stage(n_batch, wanted, pool)
+                n_batch += 1
+                if n_batch * (first_n + 256) * max(1, len(set(wanted))) > budget or n_batch >= 4096:
+                    break
+            eng.count_async(0, n_batch, [plane_of[c] for c in wanted], args.edit_distance, args.hamming, mode=0)
+            rows[k:k + n_batch] = eng.count_fetch()[1]
+            k += n_batch
+    buf = exchange_host(rows, mine, len(lanes), len(tiles), width, dist if world > 1 else None) if world == 1 else None
+    if world > 1:
+        # the counters of many batches live on the host by now: reduce them through a device tensor
+        full = exchange_host(rows, mine, len(lanes), len(tiles), width, None)
+        t = torch.from_numpy(full).to(torch.device("cuda", local))
+        dist.all_reduce(t)                      # ncclAllReduce(int64, sum) over NVLink
+        buf = t.cpu().numpy()
+    if rank == 0:
+        print_reports(sys.stdout, lanes, tiles, buf, len(targets), args.level, verbose=not args.summary_only)
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()
