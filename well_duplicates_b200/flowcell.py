@@ -94,6 +94,14 @@ def main(argv=None):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
+    report_stream = sys.stdout
+    if world > 1:
+        # stdout is the report (a compatibility surface) but native libraries write there too
+        # (NCCL prints its version banner on fd 1): keep a private handle on the real stdout
+        # and point fd 1 at stderr for the rest of the process.
+        sys.stdout.flush()
+        report_stream = os.fdopen(os.dup(1), "w")
+        os.dup2(2, 1)
     if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     say = (lambda *a: None) if (args.quiet or rank != 0) else count_cli.log
@@ -145,7 +153,8 @@ def main(argv=None):
         dist.all_reduce(t)                      # ncclAllReduce(int64, sum) over NVLink
         buf = t.cpu().numpy()
     if rank == 0:
-        print_reports(sys.stdout, lanes, tiles, buf, len(targets), args.level, verbose=not args.summary_only)
+        print_reports(report_stream, lanes, tiles, buf, len(targets), args.level, verbose=not args.summary_only)
+        report_stream.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()
