@@ -52,6 +52,9 @@ def parse():
                     help="distinct synthetic tiles kept in pinned host memory (reused round-robin for the tile slots)")
     ap.add_argument("--mode", type=int, default=0, help="0 fused kernel, 1 two-pass kernels")
     ap.add_argument("--e2e-steps", type=int, default=2)
+    ap.add_argument("--e2e-mode", default="staged", choices=["staged", "zerocopy", "both"],
+                    help="staged: every plane copied to HBM through wd_tile_put_bcl; zerocopy: planes stay in pinned "
+                         "host memory (wd_tile_map_host) and the kernel pulls the sectors it needs over PCIe")
     ap.add_argument("--cpu-tiles", type=int, default=0, help="tiles in the cpu_baseline sample (0 = 24 per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--hamming", action="store_true")
@@ -325,9 +328,38 @@ def main():
         ms = ev0.elapsed_time(ev1)
         clocks = sampler.stop(t_w0, t_w1)
 
+        # ---- e2e, zero-copy flavour: planes stay in pinned host memory ------------------
+        zc_ms = None
+        if args.e2e_steps > 0 and args.e2e_mode in ("zerocopy", "both"):
+            # one distinct pinned block per tile slot, so that no slot can hit another slot's lines in L2
+            zc = list(pins) + [PinnedArray((N_CYCLES, N_WELLS)) for _ in range(n_tiles - D)]
+            with ThreadPoolExecutor(max_workers=8) as pool:
+                list(pool.map(lambda s: np.copyto(zc[s].array, pins[s % D].array), range(D, n_tiles)))
+
+            def map_tiles():
+                for s in range(n_tiles):
+                    eng.tile_map_host(s, N_WELLS, zc[s].array)
+                    eng.tile_put_filter(s, filt_pins[s % D].array)
+
+            map_tiles()
+            zc_counters = step(True)
+            zc_ok = bool(np.array_equal(zc_counters, counters))
+            barrier()
+            ev4, ev5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            ev4.record(stream)
+            for _ in range(args.e2e_steps):
+                map_tiles()
+                res = step(True)
+            ev5.record(stream)
+            barrier()
+            zc_ms = ev4.elapsed_time(ev5) / args.e2e_steps
+            d2h_per_step = int(res.size * 8)
+            for z in zc[D:]:
+                z.free()
+
         # ---- e2e: host planes -> C ABI -> counters on the host, every step -------------
         e2e_ms = None
-        if args.e2e_steps > 0:
+        if args.e2e_steps > 0 and args.e2e_mode in ("staged", "both"):
             push_tiles()
             step(True)
             barrier()
@@ -343,10 +375,11 @@ def main():
 
     # max over ranks
     if world > 1:
-        t = torch.tensor([ms, e2e_ms or 0.0], device="cuda", dtype=torch.float64)
+        t = torch.tensor([ms, e2e_ms or 0.0, zc_ms or 0.0], device="cuda", dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms, e2e_max = float(t[0]), float(t[1])
-        e2e_ms = e2e_max if e2e_ms is not None else None
+        ms = float(t[0])
+        e2e_ms = float(t[1]) if e2e_ms is not None else None
+        zc_ms = float(t[2]) if zc_ms is not None else None
 
     ms_per_step = ms / args.steps
     targets_per_step = total_tiles * N_TARGETS
@@ -381,6 +414,11 @@ def main():
                 "h2d_bytes_per_step": int(h2d_per_step), "d2h_bytes_per_step": d2h_per_step,
                 "h2d_gb_per_s": h2d_per_step / (e2e_ms / 1e3) / 1e9},
         }
+        if zc_ms is not None:
+            line["e2e_zero_copy"] = {
+                "value": targets_per_step / (zc_ms / 1e3), "unit": "targets/s", "ms_per_step": zc_ms,
+                "counters_equal_staged": zc_ok, "host_bytes_mapped_per_step": int(n_tiles * N_CYCLES * N_WELLS),
+                "h2d_copy_bytes_per_step": int(n_tiles * N_WELLS), "d2h_bytes_per_step": d2h_per_step}
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
             n_cpu = args.cpu_tiles or 24 * cores

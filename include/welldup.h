@@ -121,6 +121,18 @@ WD_API int wd_tile_put_bcl(wd_ctx *ctx, int tile_slot, int plane, const uint8_t 
  * tile record (PF count when excluded != 0) */
 WD_API int wd_tile_put_cbcl(wd_ctx *ctx, int tile_slot, int plane, const uint8_t *nibbles,
                      uint32_t usize, uint32_t n_block, int excluded);
+/* Zero-copy staging, instead of wd_tile_begin + wd_tile_put_bcl/_cbcl: the
+ * tile's inflated planes stay where the host put them -- planes[p * stride_bytes]
+ * in page-locked memory from wd_host_alloc() -- and the counting kernels pull
+ * only the 32-byte sectors they touch across PCIe (a few per cent of a sampled
+ * tile) instead of the whole 215 MB the per-cycle slurp of
+ * bcl_direct_reader.py:333-345 moves.  kinds[p] is a WD_PLANE_* (NULL = all
+ * BCL), n_block[p] the cluster count of a CBCL block (NULL = n_clusters).  The
+ * memory must stay unchanged until the results of the last wd_count that uses
+ * the slot have been fetched.  The filter still goes through wd_tile_put_filter. */
+WD_API int wd_tile_map_host(wd_ctx *ctx, int tile_slot, uint32_t n_clusters, int n_planes,
+                     const uint8_t *planes, size_t stride_bytes, const uint8_t *kinds,
+                     const uint32_t *n_block);
 /* K3: filter byte -> rank among PF wells or -1 (Tile._get_filter_offsets, :222-253) */
 WD_API int wd_filter_offsets(wd_ctx *ctx, int tile_slot, int32_t *offsets /* n_clusters */,
                       uint32_t *passing);

@@ -55,3 +55,35 @@ extern "C" int seq_check(const uint8_t *a, const uint8_t *b, int len, int words,
     }
     return -1;
 }
+
+// Incremental prefix DP (PrefixDP): feeds b symbol by symbol with a known only
+// up to p + k, as the fused kernel does.  out[p] (p = 1..len) = pdp_band_min
+// after p symbols.
+template <int W>
+static void prefix_dp(const uint8_t *a, const uint8_t *b, int len, int k, int chunk, int *out) {
+    wd::PSeq<W> pa;
+    wd::pseq_clear(pa);
+    int known = 0;
+    wd::PrefixDP<W> s;
+    wd::pdp_init(s);
+    for (int p = 0; p < len; ++p) {
+        int need = p + k + 1 < len ? p + k + 1 : len;
+        while (known < need) {                    // a arrives in chunks, like the centre in the kernel
+            const int upto = known + chunk < len ? known + chunk : len;
+            for (; known < upto; ++known) wd::pseq_set<W>(pa, known, a[known]);
+        }
+        wd::pdp_step<W>(s, pa, known, len, p, k, b[p]);
+        out[p + 1] = wd::pdp_band_min<W>(s, len, p + 1, k);
+    }
+}
+
+extern "C" int seq_prefix_dp(const uint8_t *a, const uint8_t *b, int len, int words, int k, int chunk, int *out) {
+    switch (words) {
+        case 1: prefix_dp<1>(a, b, len, k, chunk, out); return 0;
+        case 2: prefix_dp<2>(a, b, len, k, chunk, out); return 0;
+        case 4: prefix_dp<4>(a, b, len, k, chunk, out); return 0;
+        case 8: prefix_dp<8>(a, b, len, k, chunk, out); return 0;
+        case 16: prefix_dp<16>(a, b, len, k, chunk, out); return 0;
+    }
+    return -1;
+}

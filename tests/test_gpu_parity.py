@@ -274,6 +274,64 @@ def test_medium_cbcl_mixed_vs_oracle(eng, oracle):
         eng.count(0, 1, order, 2, False, mode=0)
 
 
+def test_zero_copy_planes_equal_staged(eng, oracle):
+    """wd_tile_map_host: planes left in pinned host memory and read in place by
+    the kernels give what staged planes give (BCL, and CBCL with both block
+    kinds), for both kernel flavours and for get_seqs."""
+    R, CP = oracle
+    from well_duplicates_b200 import synth
+    from well_duplicates_b200.engine import PinnedArray
+    rng = np.random.default_rng(5)
+    n, row_len, ncyc, split = 30001, 200, 30, 11
+    X, Y = synth.hex_lattice(n, row_len)
+    centres = rng.choice(n, size=400, replace=False).astype(np.uint32)
+    woffs, widx = CP.rings_csr(X, Y, centres)
+    eng.load_targets(centres, woffs, widx, 5)
+    td = synth.make_tile(rng, n, ncyc, row_len, pf_rate=0.7, dup_rate=0.25, shift_share=0.3, nocall_rate=0.01)
+    order = list(range(ncyc))
+    # BCL
+    pin = PinnedArray((ncyc, n + 7))
+    pin.array[:, :n] = td.planes
+    eng.tile_map_host(0, n, pin.array)
+    eng.tile_put_filter(0, td.filt)
+    wpt, wc = CP.count_tile([td.planes[c] for c in order], ["bcl"] * ncyc, td.filt, centres, woffs, widx, 5, 2, False)
+    for mode in (0, 1):
+        pt, cnt = eng.count(0, 1, order, 2, False, mode=mode)
+        assert np.array_equal(pt[0], wpt) and np.array_equal(cnt[0], wc)
+    codes, pf = eng.get_seqs(0, widx[:500], order)
+    wcodes, wpf = CP.get_codes([td.planes[c] for c in order], ["bcl"] * ncyc, td.filt, widx[:500])
+    assert np.array_equal(codes, wcodes) and np.array_equal(pf, wpf)
+    with pytest.raises(ValueError):
+        eng.tile_put_bcl(0, 0, td.planes[0])                  # a mapped slot takes no copies
+    with pytest.raises(ValueError):
+        eng.tile_map_host(1, n, np.zeros((ncyc, n), np.uint8))   # pageable memory is refused
+    # CBCL, early cycles with every well, later ones PF wells only
+    pfmask = (td.filt & 1).astype(bool)
+    stride = (n + 1) // 2
+    pin2 = PinnedArray((ncyc, stride))
+    planes, kinds, n_block = [], [], []
+    for c in range(ncyc):
+        nib = synth.bcl_to_nibbles(td.planes[c])
+        excl = c >= split
+        if excl:
+            nib = nib[pfmask]
+        packed = synth.pack_nibbles(nib)
+        pin2.array[c, : packed.size] = packed
+        planes.append(packed)
+        kinds.append("cbcl_excl" if excl else "cbcl")
+        n_block.append(nib.size)
+    eng.tile_map_host(0, n, pin2.array, kinds=[CP.KIND[k] for k in kinds], n_block=n_block)
+    eng.tile_put_filter(0, td.filt)
+    wpt, wc = CP.count_tile(planes, kinds, td.filt, centres, woffs, widx, 5, 2, False)
+    for mode in (0, 1):
+        pt, cnt = eng.count(0, 1, order, 2, False, mode=mode)
+        assert np.array_equal(pt[0], wpt) and np.array_equal(cnt[0], wc)
+    with pytest.raises(AssertionError):
+        eng.tile_map_host(0, n, pin2.array, kinds=[CP.KIND[k] for k in kinds], n_block=[n + 1] * ncyc)
+    pin.free()
+    pin2.free()
+
+
 def test_dup_pair_log_rows(eng, oracle):
     """Rows behind the stderr log: (tile, target, well, distance) in reference order."""
     R, CP = oracle

@@ -21,6 +21,7 @@ def harness(tmp_path_factory):
     lib = ctypes.CDLL(so)
     lib.seq_check.argtypes = [ctypes.c_char_p, ctypes.c_char_p] + [ctypes.c_int] * 4 + [ctypes.POINTER(ctypes.c_int)] * 3
     lib.seq_first_reject.argtypes = [ctypes.c_char_p, ctypes.c_char_p] + [ctypes.c_int] * 4
+    lib.seq_prefix_dp.argtypes = [ctypes.c_char_p, ctypes.c_char_p] + [ctypes.c_int] * 4 + [ctypes.POINTER(ctypes.c_int)]
     return lib
 
 
@@ -110,3 +111,49 @@ def test_prefix_rejection_is_safe_and_useful(harness, lengths):
             fired += 0 < harness.seq_first_reject(bytes(a), bytes(b), n, w, 2, 0) <= 32
     if unrelated:
         assert fired > 0.9 * unrelated
+
+
+def _band_min_bruteforce(a, b, k):
+    """out[p] = min over |j-p| <= k of ed(b[:p], a[:j]) + |j-p|, textbook DP."""
+    n = len(a)
+    col = list(range(n + 1))                      # D[j][0] = j
+    out = [0] * (n + 1)
+    for p in range(1, n + 1):
+        new = [p] + [0] * n
+        for j in range(1, n + 1):
+            new[j] = min(col[j] + 1, new[j - 1] + 1, col[j - 1] + (a[j - 1] != b[p - 1]))
+        col = new
+        out[p] = min(col[j] + abs(j - p) for j in range(max(0, p - k), min(n, p + k) + 1))
+    return out
+
+
+@pytest.mark.parametrize("lengths", [(1, 20), (40, 64), (65, 130), (190, 260)])
+def test_incremental_prefix_dp(harness, lengths):
+    """PrefixDP of the fused kernel: exact band minimum after every symbol with the
+    centre known only k symbols ahead; never rejects a true duplicate; ends on
+    the edit distance test itself."""
+    rng = np.random.default_rng(7 + lengths[0])
+    n_cases = 150 if lengths[1] < 200 else 25
+    for _ in range(n_cases):
+        n = int(rng.integers(lengths[0], lengths[1] + 1))
+        a = [int(v) for v in rng.integers(0, 5, n)]
+        b = mutate(rng, a) if rng.random() < 0.7 else [int(v) for v in rng.integers(0, 5, n)]
+        sa = "".join("ACGTN"[v] for v in a)
+        sb = "".join("ACGTN"[v] for v in b)
+        lev = R.levenshtein(sa, sb)
+        w = words_for(n)
+        for e in (2, 3, 4, 7, 12):
+            k = e // 2
+            want = _band_min_bruteforce(a, b, k)
+            out = (ctypes.c_int * (n + 1))()
+            assert harness.seq_prefix_dp(bytes(a), bytes(b), n, w, k, int(rng.integers(1, 40)), out) == 0
+            got = list(out)
+            # values above e only have to stay above e (cells outside the band are over-estimated)
+            for p in range(1, n + 1):
+                assert (got[p] <= e) == (want[p] <= e), (sa, sb, e, p, got[p], want[p])
+                if want[p] <= e:
+                    assert got[p] == want[p]
+                    assert lev >= want[p]
+            assert (got[n] <= e) == (lev <= e)
+            if lev <= e:
+                assert all(got[p] <= e for p in range(1, n + 1)), "prefix test rejected a true duplicate"

@@ -282,6 +282,58 @@ int wd_tile_begin(wd_ctx *ctx, int tile_slot, uint32_t n_clusters, int n_planes)
     s.rank_valid = false;
     s.kind_dirty = true;
     s.has_excl = false;
+    s.mapped = nullptr;
+    return WD_OK;
+}
+
+int wd_tile_map_host(wd_ctx *ctx, int tile_slot, uint32_t n_clusters, int n_planes, const uint8_t *planes,
+                     size_t stride_bytes, const uint8_t *kinds, const uint32_t *n_block) {
+    if (ctx == nullptr || planes == nullptr) WD_FAIL(WD_E_ARG, "wd_tile_map_host: null argument");
+    if (tile_slot < 0 || tile_slot > 65535) WD_FAIL(WD_E_ARG, "wd_tile_map_host: slot %d outside 0..65535", tile_slot);
+    if (n_clusters == 0) WD_FAIL(WD_E_ARG, "wd_tile_map_host: tile has no clusters");
+    if (n_planes < 1 || n_planes > 65536) WD_FAIL(WD_E_ARG, "wd_tile_map_host: bad plane count %d", n_planes);
+    WD_CUDA(cudaSetDevice(ctx->device));
+    // the kernels dereference the host block directly: it has to be page-locked and mapped
+    cudaPointerAttributes attr;
+    cudaError_t e = cudaPointerGetAttributes(&attr, planes);
+    if (e != cudaSuccess || attr.type != cudaMemoryTypeHost || attr.devicePointer == nullptr) {
+        cudaGetLastError();
+        WD_FAIL(WD_E_ARG, "wd_tile_map_host: planes must live in pinned host memory from wd_host_alloc()");
+    }
+    for (int p = 0; p < n_planes; ++p) {
+        const int k = kinds ? kinds[p] : WD_PLANE_BCL;
+        if (k != WD_PLANE_BCL && k != WD_PLANE_CBCL && k != WD_PLANE_CBCL_EXCL)
+            WD_FAIL(WD_E_ARG, "wd_tile_map_host: plane %d has kind %d", p, k);
+        const uint64_t nb = (k == WD_PLANE_BCL || n_block == nullptr) ? n_clusters : n_block[p];
+        const uint64_t bytes = k == WD_PLANE_BCL ? nb : (nb + 1) / 2;
+        if (bytes > stride_bytes) WD_FAIL(WD_E_ASSERT, "wd_tile_map_host: plane %d needs %llu bytes, stride is %zu", p,
+                                          (unsigned long long)bytes, stride_bytes);
+        // same checks as wd_tile_put_cbcl (cbcl_read.py:130-133)
+        if (k == WD_PLANE_CBCL && nb != n_clusters)
+            WD_FAIL(WD_E_ASSERT, "CBCL block holds %llu clusters, filter says %u (cbcl_read.py:133)", (unsigned long long)nb, n_clusters);
+        if (k == WD_PLANE_CBCL_EXCL && nb > n_clusters)
+            WD_FAIL(WD_E_ASSERT, "excluded CBCL block holds %llu clusters, tile has only %u", (unsigned long long)nb, n_clusters);
+    }
+    if ((size_t)tile_slot >= ctx->slots.size()) ctx->slots.resize((size_t)tile_slot + 1);
+    TileSlot &s = ctx->slots[tile_slot];
+    const size_t fstride = ((size_t)n_clusters + 255) & ~(size_t)255;
+    if (fstride > s.filter.cap) WD_CUDA(cudaStreamSynchronize(ctx->stream));
+    WD_TRY(s.filter.reserve(fstride));
+    s.n = n_clusters;
+    s.n_planes = n_planes;
+    s.stride = stride_bytes;
+    s.kind.resize((size_t)n_planes);
+    s.n_block.resize((size_t)n_planes);
+    s.has_excl = false;
+    for (int p = 0; p < n_planes; ++p) {
+        s.kind[p] = kinds ? kinds[p] : (uint8_t)WD_PLANE_BCL;
+        s.n_block[p] = (s.kind[p] == WD_PLANE_BCL || n_block == nullptr) ? n_clusters : n_block[p];
+        if (s.kind[p] == WD_PLANE_CBCL_EXCL) s.has_excl = true;
+    }
+    s.filter_set = false;
+    s.rank_valid = false;
+    s.kind_dirty = true;
+    s.mapped = static_cast<const uint8_t *>(attr.devicePointer);
     return WD_OK;
 }
 
@@ -292,7 +344,9 @@ int wd_tile_put_filter(wd_ctx *ctx, int tile_slot, const uint8_t *bytes, uint32_
     if (n != s.n) WD_FAIL(WD_E_ASSERT, "filter holds %u clusters, tile has %u", n, s.n);
     WD_CUDA(cudaSetDevice(ctx->device));
     WD_CUDA(cudaMemcpyAsync(s.filter.p, bytes, n, cudaMemcpyHostToDevice, ctx->stream));
-    if (s.stride > n) WD_CUDA(cudaMemsetAsync(s.filter.as<uint8_t>() + n, 0, s.stride - n, ctx->stream));
+    // K3 reads whole 64-byte blocks: zero the tail (the plane stride of a mapped slot says nothing about it)
+    const size_t fstride = ((size_t)n + 255) & ~(size_t)255;
+    if (fstride > n) WD_CUDA(cudaMemsetAsync(s.filter.as<uint8_t>() + n, 0, fstride - n, ctx->stream));
     s.filter_set = true;
     s.rank_valid = false;
     return WD_OK;
@@ -302,6 +356,7 @@ int wd_tile_put_bcl(wd_ctx *ctx, int tile_slot, int plane, const uint8_t *bytes,
     WD_TRY(check_slot(ctx, tile_slot, "wd_tile_put_bcl"));
     TileSlot &s = ctx->slots[tile_slot];
     if (plane < 0 || plane >= s.n_planes) WD_FAIL(WD_E_ARG, "wd_tile_put_bcl: plane %d outside 0..%d", plane, s.n_planes - 1);
+    if (s.mapped) WD_FAIL(WD_E_ARG, "wd_tile_put_bcl: slot %d is mapped to host memory (wd_tile_map_host)", tile_slot);
     // bcl_direct_reader.py:333-338
     if (n != s.n) WD_FAIL(WD_E_ASSERT, "BCL header says %u clusters, filter says %u", n, s.n);
     WD_CUDA(cudaSetDevice(ctx->device));
@@ -317,6 +372,7 @@ int wd_tile_put_cbcl(wd_ctx *ctx, int tile_slot, int plane, const uint8_t *nibbl
     WD_TRY(check_slot(ctx, tile_slot, "wd_tile_put_cbcl"));
     TileSlot &s = ctx->slots[tile_slot];
     if (plane < 0 || plane >= s.n_planes) WD_FAIL(WD_E_ARG, "wd_tile_put_cbcl: plane %d outside 0..%d", plane, s.n_planes - 1);
+    if (s.mapped) WD_FAIL(WD_E_ARG, "wd_tile_put_cbcl: slot %d is mapped to host memory (wd_tile_map_host)", tile_slot);
     if ((uint64_t)usize * 2 < n_block) WD_FAIL(WD_E_ASSERT, "CBCL block of %u bytes cannot hold %u clusters", usize, n_block);
     if (!excluded && n_block != s.n)
         WD_FAIL(WD_E_ASSERT, "CBCL block holds %u clusters, filter says %u (cbcl_read.py:133)", n_block, s.n);

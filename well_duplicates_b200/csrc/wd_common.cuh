@@ -59,6 +59,7 @@ struct TileSlot {
     int n_planes = 0;
     size_t stride = 0;
     DevBuf planes, filter, pfmask, pfrank, kind_dev, pfcount_dev;
+    const uint8_t *mapped = nullptr;   // planes left in pinned host memory (wd_tile_map_host): device view of it
     std::vector<uint8_t> kind;
     std::vector<uint32_t> n_block;
     bool filter_set = false;

@@ -214,6 +214,94 @@ WD_HD int myers_distance(const PSeq<W> &a, const PSeq<W> &b, int len) {
     return score;
 }
 
+// Incremental form of the same dynamic programme, for the fused gather: b is
+// fed one symbol at a time (one plane byte at a time), and after p symbols the
+// column D[.][p] of the edit matrix against a is available as vertical deltas,
+//   D[j][p] = p + popc(Pv & below(j)) - popc(Mv & below(j)).
+// Lev(a, b) <= e on equal-length strings needs an alignment that crosses
+// column p at some row j with |j - p| <= k = e/2 (it has to spend |j - p|
+// indels before the crossing and as many after it), and costs at least
+// D[j][p] + |j - p|.  So  min over |j-p| <= k of D[j][p] + |j - p|  > e
+// proves dist > e from the first p symbols of b and the first p + k of a --
+// the exact prefix test; at p = len it is the distance test itself.  Rows
+// below the band never carry an alignment of cost <= e, so a needs to be known
+// only up to row p + k (unknown rows count as mismatches), and words of the
+// bit-vectors wholly below the band are left in their initial state until the
+// band reaches them (their cells then over-estimate D, which cannot create a
+// value <= e).
+template <int W>
+struct PrefixDP {
+    uint64_t Pv[W], Mv[W];
+};
+
+template <int W>
+WD_HD void pdp_init(PrefixDP<W> &s) {
+#pragma unroll
+    for (int w = 0; w < W; ++w) { s.Pv[w] = ~0ull; s.Mv[w] = 0ull; }
+}
+
+// consume b[p] = c (0..3 bases, 4 = N, anything else matches nothing); a is
+// valid over [0, known_a), known_a >= min(len, p + k + 1)
+template <int W>
+WD_HD void pdp_step(PrefixDP<W> &s, const PSeq<W> &a, int known_a, int len, int p, int k, unsigned c) {
+    const uint64_t tlo = (c & 1u) ? ~0ull : 0ull;
+    const uint64_t thi = (c & 2u) ? ~0ull : 0ull;
+    const uint64_t tn = (c & 4u) ? ~0ull : 0ull;
+    const uint64_t tany = c <= 4u ? ~0ull : 0ull;
+    const int last_w = (len - 1) >> 6;
+    const int band_w = (p + k + 1) >> 6;
+    int hin = 1;                                  // D[0][p+1] - D[0][p]
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        if (w <= last_w && w <= band_w) {
+            uint64_t Eq = (tn & a.nn[w]) | (~tn & ~a.nn[w] & ~(a.lo[w] ^ tlo) & ~(a.hi[w] ^ thi));
+            Eq &= len_mask(known_a, w) & tany;
+            const uint64_t pv = s.Pv[w], mv = s.Mv[w];
+            const uint64_t Xv = Eq | mv;
+            if (hin < 0) Eq |= 1ull;
+            const uint64_t Xh = (((Eq & pv) + pv) ^ pv) | Eq;
+            uint64_t Ph = mv | ~(Xh | pv);
+            uint64_t Mh = pv & Xh;
+            int hout = 0;
+            if (Ph >> 63) hout = 1;
+            else if (Mh >> 63) hout = -1;
+            Ph <<= 1;
+            Mh <<= 1;
+            if (hin < 0) Mh |= 1ull;
+            else if (hin > 0) Ph |= 1ull;
+            s.Pv[w] = Mh | ~(Xv | Ph);
+            s.Mv[w] = Ph & Xv;
+            hin = hout;
+        }
+    }
+}
+
+// after p symbols of b:  min over |j - p| <= k, 0 <= j <= len  of  D[j][p] + |j - p|
+template <int W>
+WD_HD int pdp_band_min(const PrefixDP<W> &s, int len, int p, int k) {
+    const int jlo = p - k > 0 ? p - k : 0;
+    const int jhi = p + k < len ? p + k : len;
+    int d = p;
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+        const uint64_t m = len_mask(jlo, w);
+        d += popc64(s.Pv[w] & m) - popc64(s.Mv[w] & m);
+    }
+    int best = d + (p - jlo);
+    for (int j = jlo; j < jhi; ++j) {             // row j -> j + 1 is bit j
+        const int w = j >> 6, b = j & 63;
+        uint64_t pv = 0, mv = 0;
+#pragma unroll
+        for (int i = 0; i < W; ++i)
+            if (i == w) { pv = s.Pv[i]; mv = s.Mv[i]; }
+        d += (int)((pv >> b) & 1ull) - (int)((mv >> b) & 1ull);
+        const int off = j + 1 - p;
+        const int v = d + (off < 0 ? -off : off);
+        best = v < best ? v : best;
+    }
+    return best;
+}
+
 // dist(a, b) <= e under the reference's chosen metric.
 template <int W>
 WD_HD bool is_duplicate(const PSeq<W> &a, const PSeq<W> &b, int len, int e, bool use_hamming) {

@@ -87,7 +87,7 @@ int filter_rank(wd_ctx *ctx, const int *slot_ids, int n) {
 
 static TileDesc make_desc(const TileSlot &s) {
     TileDesc d;
-    d.planes = s.planes.as<uint8_t>();
+    d.planes = s.mapped ? s.mapped : s.planes.as<uint8_t>();
     d.stride = s.stride;
     d.filter = s.filter.as<uint8_t>();
     d.pfmask = s.pfmask.as<uint64_t>();
@@ -371,16 +371,73 @@ compare_count_kernel(CountArgs a) {
 
 // fused flavour (production): the warp gathers and decodes its target's wells
 // straight from the planes, compares in registers and never writes the packed
-// words.
+// words.  What it reads is decided symbol by symbol:
 //  * targets whose centre fails the filter are skipped before any plane byte
 //    is read;
+//  * ring wells are read a few cycles at a time, one well per lane, and fed to
+//    the incremental edit-distance programme of wd_seq.cuh (PrefixDP; a running
+//    mismatch count for --hamming / e < 2).  A well stops being read as soon as
+//    its prefix proves dist > e -- 96 % of unrelated reads after 6 symbols --
+//    so the later planes are touched only around real duplicates;
 //  * the centre is decoded by the whole warp (lane = cycle, three ballots turn
-//    32 calls into one word of each bit-plane);
-//  * ring wells are decoded 8 cycles at a time, one well per lane, and a well
-//    stops being read as soon as its prefix proves dist > e (prefix_rejects):
-//    unrelated reads drop out after 16-24 of 50 cycles, so the later planes are
-//    touched only in the centre's row and around real duplicates.
+//    the calls into bit-plane words), CENTRE_CHUNK cycles at a time and only as
+//    far ahead as the programme needs (k = e/2 symbols past the ring wells): a
+//    target without duplicates never reads its centre beyond the first chunks.
 constexpr int FUSED_TPB = 64;    // targets per CTA; its 8 warps pull them from a shared counter
+constexpr int CENTRE_CHUNK = 16;
+
+// raw call (0 = no-call, else base = raw & 3) -> symbol 0..3, 4 = N
+__device__ __forceinline__ uint32_t call_symbol(uint32_t raw) { return raw == 0u ? 4u : (raw & 3u); }
+
+// n <= 16 bits of a W-word bit string starting at bit p
+template <int W>
+__device__ __forceinline__ uint32_t bits_at(const uint64_t *plane, int p, int n) {
+    const int w = p >> 6, sh = p & 63;
+    uint64_t v = 0;
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        if (i == w) v |= plane[i] >> sh;
+        if (i == w + 1 && sh != 0) v |= plane[i] << (64 - sh);
+    }
+    return (uint32_t)v & ((1u << n) - 1u);
+}
+
+// NMAX calls of one well at sequence positions p .. p+n-1, all loads in flight together
+template <bool ALL_BCL, int NMAX>
+__device__ __forceinline__ void load_calls(const TileDesc &d, uint32_t well, int rank, const unsigned long long *s_off,
+                                           const uint8_t *s_kind, int p, int n, uint32_t (&raw)[NMAX]) {
+#pragma unroll
+    for (int j = 0; j < NMAX; ++j) {
+        raw[j] = 0u;
+        if (j < n) raw[j] = load_call<ALL_BCL>(d, well, rank, s_off[p + j], ALL_BCL ? 0 : s_kind[p + j]);
+    }
+}
+
+template <int W, bool ALL_BCL, int NMAX>
+__device__ __forceinline__ bool ring_round(const TileDesc &d, uint32_t well, int rank, const unsigned long long *s_off,
+                                           const uint8_t *s_kind, const PSeq<W> &c, int known_c, int len, int p, int n,
+                                           int k, int e, bool ham_like, PrefixDP<W> &dp, int &mism) {
+    uint32_t raw[NMAX];
+    load_calls<ALL_BCL, NMAX>(d, well, rank, s_off, s_kind, p, n, raw);
+    if (ham_like) {
+        uint32_t glo = 0, ghi = 0, gnn = 0;
+#pragma unroll
+        for (int j = 0; j < NMAX; ++j) {
+            if (j < n) {
+                const uint32_t sym = call_symbol(raw[j]);
+                glo |= (sym & 1u) << j;
+                ghi |= ((sym >> 1) & 1u) << j;
+                gnn |= (sym >> 2) << j;
+            }
+        }
+        mism += __popc((bits_at<W>(c.lo, p, n) ^ glo) | (bits_at<W>(c.hi, p, n) ^ ghi) | (bits_at<W>(c.nn, p, n) ^ gnn));
+        return mism <= e;
+    }
+#pragma unroll
+    for (int j = 0; j < NMAX; ++j)
+        if (j < n) pdp_step<W>(dp, c, known_c, len, p + j, k, call_symbol(raw[j]));
+    return pdp_band_min<W>(dp, len, p + n, k) <= e;
+}
 
 template <int W, int LMAX, bool ALL_BCL>
 __global__ void __launch_bounds__(CNT_WARPS * 32)
@@ -395,7 +452,11 @@ fused_count_kernel(CountArgs a) {
     const int lane = threadIdx.x & 31;
     const uint32_t tile = blockIdx.y;
     const TileDesc d = a.descs[tile];
-    const bool ham = a.hamming != 0;
+    const int len = a.len, e = a.e;
+    // Levenshtein <= 1 <=> Hamming <= 1 on equal lengths (an indel pair costs 2)
+    const bool ham_like = a.hamming != 0 || e < 2;
+    const int k = ham_like ? 0 : (e >> 1);
+    const bool read_nothing = e < 0 || e >= len;       // no pair / every pair is a duplicate
     const uint32_t t_begin = blockIdx.x * FUSED_TPB;
     const uint32_t t_end = min(t_begin + FUSED_TPB, a.t);
     // Targets differ a lot in cost (a failed centre costs one byte, a real
@@ -413,29 +474,11 @@ fused_count_kernel(CountArgs a) {
 #pragma unroll
         for (int l = 0; l < LMAX; ++l) dups[l] = 0;
         if (valid) {
-            // ---- centre: lane = cycle ------------------------------------------------
             PSeq<W> c;
-            {
-                int crank = 0;
-                if (!ALL_BCL && (d.flags & 1u)) crank = pf_rank(d, centre);
-#pragma unroll
-                for (int w = 0; w < W; ++w) {
-                    uint32_t lo2[2], hi2[2], nn2[2];
-#pragma unroll
-                    for (int h = 0; h < 2; ++h) {
-                        const int p = 64 * w + 32 * h + lane;
-                        uint32_t code = 4u;
-                        if (p < a.len) code = load_call<ALL_BCL>(d, centre, crank, s_off[p], ALL_BCL ? 0 : s_kind[p]);
-                        lo2[h] = __ballot_sync(0xffffffffu, code & 1u);
-                        hi2[h] = __ballot_sync(0xffffffffu, code & 2u);
-                        nn2[h] = __ballot_sync(0xffffffffu, code == 0u);
-                    }
-                    c.lo[w] = (uint64_t)lo2[0] | ((uint64_t)lo2[1] << 32);
-                    c.hi[w] = (uint64_t)hi2[0] | ((uint64_t)hi2[1] << 32);
-                    c.nn[w] = (uint64_t)nn2[0] | ((uint64_t)nn2[1] << 32);
-                }
-            }
-            // ---- ring wells: lane = well; 16 cycles, then 8 at a time with early exit ------
+            pseq_clear(c);
+            int known_c = 0;
+            int crank = 0;
+            if (!ALL_BCL && (d.flags & 1u)) crank = pf_rank(d, centre);
             for (uint32_t base = s0 + 1; base < s1; base += 32) {
                 const uint32_t s = base + lane;
                 const bool mine = s < s1;
@@ -446,28 +489,37 @@ fused_count_kernel(CountArgs a) {
                     lvl = __ldg(a.slot_level + s);
                     if (!ALL_BCL && (d.flags & 1u)) rank = pf_rank(d, well);
                 }
-                PSeq<W> b;
-                pseq_clear(b);
-                bool alive = mine;
-                int p = 0;
-                while (p < a.len) {
+                PrefixDP<W> dp;
+                pdp_init(dp);
+                int mism = 0;
+                bool alive = mine && e >= 0;
+                int p = read_nothing ? len : 0;
+                while (p < len) {
                     if (!__any_sync(0xffffffffu, alive)) break;
-                    // cycles read before the next test: a.step0 for the first round (the
-                    // Levenshtein bound is too weak to drop anything after 8 symbols), a.step1 after
-                    const int step = p == 0 ? a.step0 : a.step1;
-                    if (alive) {
-                        uint32_t glo, ghi, gnn;
-                        if (step == 16) decode_n<ALL_BCL, 16>(d, well, rank, s_off, s_kind, p, a.len, glo, ghi, gnn);
-                        else if (step == 8) decode_n<ALL_BCL, 8>(d, well, rank, s_off, s_kind, p, a.len, glo, ghi, gnn);
-                        else if (step == 4) decode_n<ALL_BCL, 4>(d, well, rank, s_off, s_kind, p, a.len, glo, ghi, gnn);
-                        else decode_n<ALL_BCL, 2>(d, well, rank, s_off, s_kind, p, a.len, glo, ghi, gnn);
-                        pseq_or_group<W>(b, p, glo, ghi, gnn);
-                        const int known = min(p + step, a.len);
-                        if (known < a.len && prefix_rejects<W>(c, b, a.len, known, a.e, ham)) alive = false;
+                    const int n = min(p == 0 ? a.step0 : a.step1, len - p);
+                    // ---- centre: lane = cycle, as far as this round looks ahead ----------
+                    const int need = min(len, p + n + k);
+                    while (known_c < need) {
+                        const int q = known_c + lane;
+                        uint32_t sym = 0u;
+                        if (lane < CENTRE_CHUNK && q < len)
+                            sym = call_symbol(load_call<ALL_BCL>(d, centre, crank, s_off[q], ALL_BCL ? 0 : s_kind[q]));
+                        const uint32_t glo = __ballot_sync(0xffffffffu, sym & 1u);
+                        const uint32_t ghi = __ballot_sync(0xffffffffu, sym & 2u);
+                        const uint32_t gnn = __ballot_sync(0xffffffffu, sym & 4u);
+                        pseq_or_group<W>(c, known_c, glo, ghi, gnn);     // chunks never straddle a word
+                        known_c = min(len, known_c + CENTRE_CHUNK);
                     }
-                    p += step;
+                    // ---- ring wells: lane = well ---------------------------------------------
+                    if (alive) {
+                        if (n > 8) alive = ring_round<W, ALL_BCL, 16>(d, well, rank, s_off, s_kind, c, known_c, len, p, n, k, e, ham_like, dp, mism);
+                        else if (n > 4) alive = ring_round<W, ALL_BCL, 8>(d, well, rank, s_off, s_kind, c, known_c, len, p, n, k, e, ham_like, dp, mism);
+                        else if (n > 2) alive = ring_round<W, ALL_BCL, 4>(d, well, rank, s_off, s_kind, c, known_c, len, p, n, k, e, ham_like, dp, mism);
+                        else alive = ring_round<W, ALL_BCL, 2>(d, well, rank, s_off, s_kind, c, known_c, len, p, n, k, e, ham_like, dp, mism);
+                    }
+                    p += n;
                 }
-                const bool dup = alive && is_duplicate<W>(c, b, a.len, a.e, ham);
+                const bool dup = alive;            // survived to p == len: dist <= e
 #pragma unroll
                 for (int l = 0; l < LMAX; ++l)
                     if (l < a.levels) dups[l] += __popc(__ballot_sync(0xffffffffu, dup && lvl == l + 1));
@@ -717,11 +769,11 @@ int count_async(wd_ctx *ctx, int first_slot, int n_tiles, const int32_t *order, 
     // early-exit schedule of the fused kernel (cycles read per round: first, later), from the sweep
     // in profiles/r01_early_exit_sweep.txt: short rounds win -- the traffic saved by dropping a well
     // sooner outweighs the extra dependent round trips
-    a.step0 = (hamming || e < 2) ? 4 : 8;
-    a.step1 = 4;
+    a.step0 = 6;
+    a.step1 = 2;
     if (const char *sch = getenv("WELLDUP_STEPS")) {
         int s0 = 0, s1 = 0;
-        if (sscanf(sch, "%d,%d", &s0, &s1) == 2 && (s0 == 2 || s0 == 4 || s0 == 8 || s0 == 16) && (s1 == 2 || s1 == 4 || s1 == 8) && s0 % s1 == 0) {
+        if (sscanf(sch, "%d,%d", &s0, &s1) == 2 && s0 >= 1 && s0 <= 16 && s1 >= 1 && s1 <= 16) {
             a.step0 = s0;
             a.step1 = s1;
         }
