@@ -58,6 +58,8 @@ def parse():
     ap.add_argument("--cpu-tiles", type=int, default=0, help="tiles in the cpu_baseline sample (0 = 24 per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--hamming", action="store_true")
+    ap.add_argument("--sweep-steps", default="", help="early-exit schedules to time in this process, e.g. '8,4;8,2;6,2' "
+                                                      "(sets WELLDUP_STEPS; resident planes, and zero-copy when --e2e-mode asks)")
     ap.add_argument("--l2-fetch", type=int, default=0, help="override cudaLimitMaxL2FetchGranularity (32/64/128)")
     return ap.parse_args()
 
@@ -328,18 +330,38 @@ def main():
         ms = ev0.elapsed_time(ev1)
         clocks = sampler.stop(t_w0, t_w1)
 
+        def timed(fn, n):
+            barrier()
+            a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            a.record(stream)
+            for _ in range(n):
+                fn()
+            b.record(stream)
+            barrier()
+            return a.elapsed_time(b) / n
+
+        sweep = {}
+        schedules = [x for x in args.sweep_steps.split(";") if x]
+        for sch in schedules:
+            os.environ["WELLDUP_STEPS"] = sch
+            step(False)
+            sweep[sch] = {"resident_ms": timed(lambda: step(False), args.steps)}
+        os.environ.pop("WELLDUP_STEPS", None)
+
         # ---- e2e, zero-copy flavour: planes stay in pinned host memory ------------------
         zc_ms = None
         if args.e2e_steps > 0 and args.e2e_mode in ("zerocopy", "both"):
             # one distinct pinned block per tile slot, so that no slot can hit another slot's lines in L2
             zc = list(pins) + [PinnedArray((N_CYCLES, N_WELLS)) for _ in range(n_tiles - D)]
+            zc_filt = list(filt_pins) + [PinnedArray((N_WELLS,)) for _ in range(n_tiles - D)]
             with ThreadPoolExecutor(max_workers=8) as pool:
                 list(pool.map(lambda s: np.copyto(zc[s].array, pins[s % D].array), range(D, n_tiles)))
+            for s in range(D, n_tiles):
+                zc_filt[s].array[:] = filt_pins[s % D].array
 
             def map_tiles():
                 for s in range(n_tiles):
-                    eng.tile_map_host(s, N_WELLS, zc[s].array)
-                    eng.tile_put_filter(s, filt_pins[s % D].array)
+                    eng.tile_map_host(s, N_WELLS, zc[s].array, pinned_filter=zc_filt[s].array)
 
             map_tiles()
             zc_counters = step(True)
@@ -354,6 +376,15 @@ def main():
             barrier()
             zc_ms = ev4.elapsed_time(ev5) / args.e2e_steps
             d2h_per_step = int(res.size * 8)
+
+            def zc_step():
+                map_tiles()
+                step(True)
+            for sch in schedules:
+                os.environ["WELLDUP_STEPS"] = sch
+                zc_step()
+                sweep[sch]["zero_copy_ms"] = timed(zc_step, args.e2e_steps)
+            os.environ.pop("WELLDUP_STEPS", None)
             for z in zc[D:]:
                 z.free()
 
@@ -414,11 +445,13 @@ def main():
                 "h2d_bytes_per_step": int(h2d_per_step), "d2h_bytes_per_step": d2h_per_step,
                 "h2d_gb_per_s": h2d_per_step / (e2e_ms / 1e3) / 1e9},
         }
+        if sweep:
+            line["sweep_steps"] = sweep
         if zc_ms is not None:
             line["e2e_zero_copy"] = {
                 "value": targets_per_step / (zc_ms / 1e3), "unit": "targets/s", "ms_per_step": zc_ms,
                 "counters_equal_staged": zc_ok, "host_bytes_mapped_per_step": int(n_tiles * N_CYCLES * N_WELLS),
-                "h2d_copy_bytes_per_step": int(n_tiles * N_WELLS), "d2h_bytes_per_step": d2h_per_step}
+                "h2d_copy_bytes_per_step": 0, "d2h_bytes_per_step": d2h_per_step}
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
             n_cpu = args.cpu_tiles or 24 * cores

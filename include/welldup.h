@@ -129,10 +129,11 @@ WD_API int wd_tile_put_cbcl(wd_ctx *ctx, int tile_slot, int plane, const uint8_t
  * bcl_direct_reader.py:333-345 moves.  kinds[p] is a WD_PLANE_* (NULL = all
  * BCL), n_block[p] the cluster count of a CBCL block (NULL = n_clusters).  The
  * memory must stay unchanged until the results of the last wd_count that uses
- * the slot have been fetched.  The filter still goes through wd_tile_put_filter. */
+ * the slot have been fetched.  filter (n_clusters bytes, body of the .filter
+ * file) may be mapped the same way, or NULL: then wd_tile_put_filter supplies it. */
 WD_API int wd_tile_map_host(wd_ctx *ctx, int tile_slot, uint32_t n_clusters, int n_planes,
                      const uint8_t *planes, size_t stride_bytes, const uint8_t *kinds,
-                     const uint32_t *n_block);
+                     const uint32_t *n_block, const uint8_t *filter);
 /* K3: filter byte -> rank among PF wells or -1 (Tile._get_filter_offsets, :222-253) */
 WD_API int wd_filter_offsets(wd_ctx *ctx, int tile_slot, int32_t *offsets /* n_clusters */,
                       uint32_t *passing);

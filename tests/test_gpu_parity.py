@@ -320,16 +320,25 @@ def test_zero_copy_planes_equal_staged(eng, oracle):
         planes.append(packed)
         kinds.append("cbcl_excl" if excl else "cbcl")
         n_block.append(nib.size)
-    eng.tile_map_host(0, n, pin2.array, kinds=[CP.KIND[k] for k in kinds], n_block=n_block)
-    eng.tile_put_filter(0, td.filt)
     wpt, wc = CP.count_tile(planes, kinds, td.filt, centres, woffs, widx, 5, 2, False)
-    for mode in (0, 1):
-        pt, cnt = eng.count(0, 1, order, 2, False, mode=mode)
-        assert np.array_equal(pt[0], wpt) and np.array_equal(cnt[0], wc)
+    pinf = PinnedArray((n,))
+    pinf.array[:] = td.filt
+    for mapped_filter in (False, True):
+        eng.tile_map_host(0, n, pin2.array, kinds=[CP.KIND[k] for k in kinds], n_block=n_block,
+                          pinned_filter=pinf.array if mapped_filter else None)
+        if not mapped_filter:
+            eng.tile_put_filter(0, td.filt)
+        for mode in (0, 1):
+            pt, cnt = eng.count(0, 1, order, 2, False, mode=mode)
+            assert np.array_equal(pt[0], wpt) and np.array_equal(cnt[0], wc)
+        off, passing = eng.filter_offsets(0)
+        woff, wpass = CP.filter_offsets(td.filt)
+        assert np.array_equal(off, woff) and passing == wpass
     with pytest.raises(AssertionError):
         eng.tile_map_host(0, n, pin2.array, kinds=[CP.KIND[k] for k in kinds], n_block=[n + 1] * ncyc)
     pin.free()
     pin2.free()
+    pinf.free()
 
 
 def test_dup_pair_log_rows(eng, oracle):

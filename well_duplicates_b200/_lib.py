@@ -49,7 +49,7 @@ SIGNATURES = {
     "wd_tile_put_filter": (C.c_int, [_p, C.c_int, _p, C.c_uint32]),
     "wd_tile_put_bcl": (C.c_int, [_p, C.c_int, C.c_int, _p, C.c_uint32]),
     "wd_tile_put_cbcl": (C.c_int, [_p, C.c_int, C.c_int, _p, C.c_uint32, C.c_uint32, C.c_int]),
-    "wd_tile_map_host": (C.c_int, [_p, C.c_int, C.c_uint32, C.c_int, _p, C.c_size_t, _p, _p]),
+    "wd_tile_map_host": (C.c_int, [_p, C.c_int, C.c_uint32, C.c_int, _p, C.c_size_t, _p, _p, _p]),
     "wd_filter_offsets": (C.c_int, [_p, C.c_int, _p, _u32p]),
     "wd_get_seqs": (C.c_int, [_p, C.c_int, _p, C.c_uint32, _p, C.c_int, _p, _p]),
     "wd_count": (C.c_int, [_p, C.c_int, C.c_int, _p, C.c_int, C.c_int, C.c_int, C.c_int, _p, _p]),

@@ -283,11 +283,13 @@ int wd_tile_begin(wd_ctx *ctx, int tile_slot, uint32_t n_clusters, int n_planes)
     s.kind_dirty = true;
     s.has_excl = false;
     s.mapped = nullptr;
+    s.mapped_filter = nullptr;
+    s.mapped_filter_host = nullptr;
     return WD_OK;
 }
 
 int wd_tile_map_host(wd_ctx *ctx, int tile_slot, uint32_t n_clusters, int n_planes, const uint8_t *planes,
-                     size_t stride_bytes, const uint8_t *kinds, const uint32_t *n_block) {
+                     size_t stride_bytes, const uint8_t *kinds, const uint32_t *n_block, const uint8_t *filter) {
     if (ctx == nullptr || planes == nullptr) WD_FAIL(WD_E_ARG, "wd_tile_map_host: null argument");
     if (tile_slot < 0 || tile_slot > 65535) WD_FAIL(WD_E_ARG, "wd_tile_map_host: slot %d outside 0..65535", tile_slot);
     if (n_clusters == 0) WD_FAIL(WD_E_ARG, "wd_tile_map_host: tile has no clusters");
@@ -299,6 +301,14 @@ int wd_tile_map_host(wd_ctx *ctx, int tile_slot, uint32_t n_clusters, int n_plan
     if (e != cudaSuccess || attr.type != cudaMemoryTypeHost || attr.devicePointer == nullptr) {
         cudaGetLastError();
         WD_FAIL(WD_E_ARG, "wd_tile_map_host: planes must live in pinned host memory from wd_host_alloc()");
+    }
+    cudaPointerAttributes fattr;
+    if (filter != nullptr) {
+        e = cudaPointerGetAttributes(&fattr, filter);
+        if (e != cudaSuccess || fattr.type != cudaMemoryTypeHost || fattr.devicePointer == nullptr) {
+            cudaGetLastError();
+            WD_FAIL(WD_E_ARG, "wd_tile_map_host: filter must live in pinned host memory from wd_host_alloc()");
+        }
     }
     for (int p = 0; p < n_planes; ++p) {
         const int k = kinds ? kinds[p] : WD_PLANE_BCL;
@@ -330,10 +340,12 @@ int wd_tile_map_host(wd_ctx *ctx, int tile_slot, uint32_t n_clusters, int n_plan
         s.n_block[p] = (s.kind[p] == WD_PLANE_BCL || n_block == nullptr) ? n_clusters : n_block[p];
         if (s.kind[p] == WD_PLANE_CBCL_EXCL) s.has_excl = true;
     }
-    s.filter_set = false;
+    s.filter_set = filter != nullptr;
     s.rank_valid = false;
     s.kind_dirty = true;
     s.mapped = static_cast<const uint8_t *>(attr.devicePointer);
+    s.mapped_filter = filter ? static_cast<const uint8_t *>(fattr.devicePointer) : nullptr;
+    s.mapped_filter_host = filter;
     return WD_OK;
 }
 
@@ -349,6 +361,8 @@ int wd_tile_put_filter(wd_ctx *ctx, int tile_slot, const uint8_t *bytes, uint32_
     if (fstride > n) WD_CUDA(cudaMemsetAsync(s.filter.as<uint8_t>() + n, 0, fstride - n, ctx->stream));
     s.filter_set = true;
     s.rank_valid = false;
+    s.mapped_filter = nullptr;
+    s.mapped_filter_host = nullptr;
     return WD_OK;
 }
 

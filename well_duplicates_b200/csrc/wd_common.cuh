@@ -60,6 +60,8 @@ struct TileSlot {
     size_t stride = 0;
     DevBuf planes, filter, pfmask, pfrank, kind_dev, pfcount_dev;
     const uint8_t *mapped = nullptr;   // planes left in pinned host memory (wd_tile_map_host): device view of it
+    const uint8_t *mapped_filter = nullptr;   // same for the filter bytes (optional)
+    const uint8_t *mapped_filter_host = nullptr;
     std::vector<uint8_t> kind;
     std::vector<uint32_t> n_block;
     bool filter_set = false;

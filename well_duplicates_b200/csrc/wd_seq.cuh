@@ -229,46 +229,69 @@ WD_HD int myers_distance(const PSeq<W> &a, const PSeq<W> &b, int len) {
 // bit-vectors wholly below the band are left in their initial state until the
 // band reaches them (their cells then over-estimate D, which cannot create a
 // value <= e).
+// The vectors are kept as 32-bit words (two per 64-symbol word of a): 32-bit
+// adds and logic ops are single instructions on the GPU, and with the lazy
+// activation above the first rounds of a 50-symbol comparison touch one word.
+WD_HD int popc32(uint32_t v) {
+#if defined(__CUDA_ARCH__)
+    return __popc(v);
+#else
+    return __builtin_popcount(v);
+#endif
+}
+
+// valid-bit mask of 32-bit word w for a prefix of n symbols
+WD_HD uint32_t len_mask32(int n, int w) {
+    const int rem = n - 32 * w;
+    if (rem >= 32) return ~0u;
+    if (rem <= 0) return 0u;
+    return (1u << rem) - 1u;
+}
+
 template <int W>
 struct PrefixDP {
-    uint64_t Pv[W], Mv[W];
+    uint32_t Pv[2 * W], Mv[2 * W];
 };
 
 template <int W>
 WD_HD void pdp_init(PrefixDP<W> &s) {
 #pragma unroll
-    for (int w = 0; w < W; ++w) { s.Pv[w] = ~0ull; s.Mv[w] = 0ull; }
+    for (int w = 0; w < 2 * W; ++w) { s.Pv[w] = ~0u; s.Mv[w] = 0u; }
 }
 
 // consume b[p] = c (0..3 bases, 4 = N, anything else matches nothing); a is
 // valid over [0, known_a), known_a >= min(len, p + k + 1)
 template <int W>
 WD_HD void pdp_step(PrefixDP<W> &s, const PSeq<W> &a, int known_a, int len, int p, int k, unsigned c) {
-    const uint64_t tlo = (c & 1u) ? ~0ull : 0ull;
-    const uint64_t thi = (c & 2u) ? ~0ull : 0ull;
-    const uint64_t tn = (c & 4u) ? ~0ull : 0ull;
-    const uint64_t tany = c <= 4u ? ~0ull : 0ull;
-    const int last_w = (len - 1) >> 6;
-    const int band_w = (p + k + 1) >> 6;
+    const uint32_t tlo = (c & 1u) ? ~0u : 0u;
+    const uint32_t thi = (c & 2u) ? ~0u : 0u;
+    const uint32_t tn = (c & 4u) ? ~0u : 0u;
+    const uint32_t tany = c <= 4u ? ~0u : 0u;
+    const int last_w = (len - 1) >> 5;
+    const int band_w = (p + k + 1) >> 5;
     int hin = 1;                                  // D[0][p+1] - D[0][p]
 #pragma unroll
-    for (int w = 0; w < W; ++w) {
+    for (int w = 0; w < 2 * W; ++w) {
         if (w <= last_w && w <= band_w) {
-            uint64_t Eq = (tn & a.nn[w]) | (~tn & ~a.nn[w] & ~(a.lo[w] ^ tlo) & ~(a.hi[w] ^ thi));
-            Eq &= len_mask(known_a, w) & tany;
-            const uint64_t pv = s.Pv[w], mv = s.Mv[w];
-            const uint64_t Xv = Eq | mv;
-            if (hin < 0) Eq |= 1ull;
-            const uint64_t Xh = (((Eq & pv) + pv) ^ pv) | Eq;
-            uint64_t Ph = mv | ~(Xh | pv);
-            uint64_t Mh = pv & Xh;
+            const uint32_t alo = (uint32_t)(a.lo[w >> 1] >> (32 * (w & 1)));
+            const uint32_t ahi = (uint32_t)(a.hi[w >> 1] >> (32 * (w & 1)));
+            const uint32_t ann = (uint32_t)(a.nn[w >> 1] >> (32 * (w & 1)));
+            // canonical form (N carries no base bits): equal symbols <=> equal in all three planes
+            uint32_t Eq = ~((alo ^ tlo) | (ahi ^ thi) | (ann ^ tn));
+            Eq &= len_mask32(known_a, w) & tany;
+            const uint32_t pv = s.Pv[w], mv = s.Mv[w];
+            const uint32_t Xv = Eq | mv;
+            if (hin < 0) Eq |= 1u;
+            const uint32_t Xh = (((Eq & pv) + pv) ^ pv) | Eq;
+            uint32_t Ph = mv | ~(Xh | pv);
+            uint32_t Mh = pv & Xh;
             int hout = 0;
-            if (Ph >> 63) hout = 1;
-            else if (Mh >> 63) hout = -1;
+            if (Ph >> 31) hout = 1;
+            else if (Mh >> 31) hout = -1;
             Ph <<= 1;
             Mh <<= 1;
-            if (hin < 0) Mh |= 1ull;
-            else if (hin > 0) Ph |= 1ull;
+            if (hin < 0) Mh |= 1u;
+            else if (hin > 0) Ph |= 1u;
             s.Pv[w] = Mh | ~(Xv | Ph);
             s.Mv[w] = Ph & Xv;
             hin = hout;
@@ -283,18 +306,18 @@ WD_HD int pdp_band_min(const PrefixDP<W> &s, int len, int p, int k) {
     const int jhi = p + k < len ? p + k : len;
     int d = p;
 #pragma unroll
-    for (int w = 0; w < W; ++w) {
-        const uint64_t m = len_mask(jlo, w);
-        d += popc64(s.Pv[w] & m) - popc64(s.Mv[w] & m);
+    for (int w = 0; w < 2 * W; ++w) {
+        const uint32_t m = len_mask32(jlo, w);
+        d += popc32(s.Pv[w] & m) - popc32(s.Mv[w] & m);
     }
     int best = d + (p - jlo);
     for (int j = jlo; j < jhi; ++j) {             // row j -> j + 1 is bit j
-        const int w = j >> 6, b = j & 63;
-        uint64_t pv = 0, mv = 0;
+        const int w = j >> 5, b = j & 31;
+        uint32_t pv = 0, mv = 0;
 #pragma unroll
-        for (int i = 0; i < W; ++i)
+        for (int i = 0; i < 2 * W; ++i)
             if (i == w) { pv = s.Pv[i]; mv = s.Mv[i]; }
-        d += (int)((pv >> b) & 1ull) - (int)((mv >> b) & 1ull);
+        d += (int)((pv >> b) & 1u) - (int)((mv >> b) & 1u);
         const int off = j + 1 - p;
         const int v = d + (off < 0 ? -off : off);
         best = v < best ? v : best;

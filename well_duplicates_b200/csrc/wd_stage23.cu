@@ -18,6 +18,7 @@
 
 #include <cstdio>
 #include <cstdlib>
+#include <cstring>
 
 namespace wd {
 
@@ -71,6 +72,12 @@ int filter_rank(wd_ctx *ctx, const int *slot_ids, int n) {
         if (s.rank_valid) continue;
         if (!s.filter_set) WD_FAIL(WD_E_ARG, "tile slot %d has no filter loaded", slot_ids[k]);
         const uint32_t nb = (s.n + 63) / 64;
+        if (s.mapped_filter) {
+            // K3 reads whole zero-padded 64-byte blocks: bring a mapped filter into HBM first
+            const size_t fstride = ((size_t)s.n + 255) & ~(size_t)255;
+            WD_CUDA(cudaMemcpyAsync(s.filter.p, s.mapped_filter_host, s.n, cudaMemcpyHostToDevice, st));
+            if (fstride > s.n) WD_CUDA(cudaMemsetAsync(s.filter.as<uint8_t>() + s.n, 0, fstride - s.n, st));
+        }
         WD_TRY(s.pfmask.reserve((size_t)nb * 8));
         WD_TRY(s.pfrank.reserve(((size_t)nb + 1) * 4));
         WD_TRY(s.pfcount_dev.reserve((size_t)nb * 4));
@@ -89,7 +96,7 @@ static TileDesc make_desc(const TileSlot &s) {
     TileDesc d;
     d.planes = s.mapped ? s.mapped : s.planes.as<uint8_t>();
     d.stride = s.stride;
-    d.filter = s.filter.as<uint8_t>();
+    d.filter = s.mapped_filter ? s.mapped_filter : s.filter.as<uint8_t>();
     d.pfmask = s.pfmask.as<uint64_t>();
     d.pfrank = s.pfrank.as<uint32_t>();
     d.kind = s.kind_dev.as<uint8_t>();
@@ -665,7 +672,8 @@ int get_seqs(wd_ctx *ctx, int slot, const int64_t *indices, uint32_t n_idx, cons
         // zero-length range: only the flags
         WD_TRY(filter_rank(ctx, &slot, 1));
         std::vector<uint8_t> f(s.n);
-        WD_CUDA(cudaMemcpyAsync(f.data(), s.filter.p, s.n, cudaMemcpyDeviceToHost, st));
+        if (s.mapped_filter_host) memcpy(f.data(), s.mapped_filter_host, s.n);
+        else WD_CUDA(cudaMemcpyAsync(f.data(), s.filter.p, s.n, cudaMemcpyDeviceToHost, st));
         WD_CUDA(cudaStreamSynchronize(st));
         for (uint32_t i = 0; i < n_idx; ++i) pf[i] = f[wells[i]] & 1;
         return WD_OK;
@@ -769,8 +777,12 @@ int count_async(wd_ctx *ctx, int first_slot, int n_tiles, const int32_t *order, 
     // early-exit schedule of the fused kernel (cycles read per round: first, later), from the sweep
     // in profiles/r01_early_exit_sweep.txt: short rounds win -- the traffic saved by dropping a well
     // sooner outweighs the extra dependent round trips
-    a.step0 = 6;
-    a.step1 = 2;
+    // early-exit schedule (cycles read per round: first, later), from the sweeps in profiles/: planes in
+    // HBM are bound by instruction issue and latency -> few long rounds; planes pulled across PCIe
+    // (wd_tile_map_host) are bound by the number of sector requests -> many short rounds
+    const bool over_pcie = ctx->slots[first_slot].mapped != nullptr;
+    a.step0 = over_pcie ? 4 : 8;
+    a.step1 = over_pcie ? 1 : 2;
     if (const char *sch = getenv("WELLDUP_STEPS")) {
         int s0 = 0, s1 = 0;
         if (sscanf(sch, "%d,%d", &s0, &s1) == 2 && s0 >= 1 && s0 <= 16 && s1 >= 1 && s1 <= 16) {

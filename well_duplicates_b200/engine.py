@@ -136,9 +136,10 @@ class Engine:
         _lib.check(self._lib.wd_tile_put_cbcl(self._h, slot, plane, _ptr(nibbles), nibbles.size, int(n_block),
                                               1 if excluded else 0))
 
-    def tile_map_host(self, slot, n_clusters, pinned_planes, kinds=None, n_block=None):
+    def tile_map_host(self, slot, n_clusters, pinned_planes, kinds=None, n_block=None, pinned_filter=None):
         """Zero-copy staging: `pinned_planes` is a 2-D uint8 view [n_planes, stride] of a
-        PinnedArray; the kernels read it in place across PCIe."""
+        PinnedArray (`pinned_filter` optionally the filter bytes, likewise pinned); the
+        kernels read them in place across PCIe."""
         a = pinned_planes
         if a.dtype != np.uint8 or a.ndim != 2 or not a.flags.c_contiguous:
             raise ValueError("tile_map_host wants a C-contiguous 2-D uint8 array in pinned memory")
@@ -146,7 +147,8 @@ class Engine:
         n_block = None if n_block is None else _c(n_block, np.uint32)
         _lib.check(self._lib.wd_tile_map_host(self._h, slot, int(n_clusters), a.shape[0], _ptr(a), a.shape[1],
                                               None if kinds is None else _ptr(kinds),
-                                              None if n_block is None else _ptr(n_block)))
+                                              None if n_block is None else _ptr(n_block),
+                                              None if pinned_filter is None else _ptr(pinned_filter)))
         self._slots[slot] = (int(n_clusters), int(a.shape[0]))
 
     def filter_offsets(self, slot):
