@@ -342,11 +342,21 @@ def main():
 
         sweep = {}
         schedules = [x for x in args.sweep_steps.split(";") if x]
+        def set_schedule(sch):
+            # "first,later" or "first,later,centre_chunk"; None restores the library's defaults
+            os.environ.pop("WELLDUP_STEPS", None)
+            os.environ.pop("WELLDUP_CENTRE_CHUNK", None)
+            if sch:
+                f = sch.split(",")
+                os.environ["WELLDUP_STEPS"] = ",".join(f[:2])
+                if len(f) > 2:
+                    os.environ["WELLDUP_CENTRE_CHUNK"] = f[2]
+
         for sch in schedules:
-            os.environ["WELLDUP_STEPS"] = sch
+            set_schedule(sch)
             step(False)
             sweep[sch] = {"resident_ms": timed(lambda: step(False), args.steps)}
-        os.environ.pop("WELLDUP_STEPS", None)
+        set_schedule(None)
 
         # ---- e2e, zero-copy flavour: planes stay in pinned host memory ------------------
         zc_ms = None
@@ -381,10 +391,10 @@ def main():
                 map_tiles()
                 step(True)
             for sch in schedules:
-                os.environ["WELLDUP_STEPS"] = sch
+                set_schedule(sch)
                 zc_step()
                 sweep[sch]["zero_copy_ms"] = timed(zc_step, args.e2e_steps)
-            os.environ.pop("WELLDUP_STEPS", None)
+            set_schedule(None)
             for z in zc[D:]:
                 z.free()
 

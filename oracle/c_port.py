@@ -115,3 +115,15 @@ def count_tile(planes, kinds, filt, centres, level_offsets, idx, levels, edit_di
                          _p(idx), C.c_uint32(t), levels, edit_distance, 1 if use_hamming else 0,
                          _p(pt) if want_per_target else None, _p(counters))
     return pt, counters
+
+
+def count_exhaustive(X, Y, planes, kinds, filt, levels=5, edit_distance=2, use_hamming=False):
+    """Exhaustive mode: every well of the tile is a target (what
+    prepare_cluster_indexes.py -n <wells> followed by count_well_duplicates.py
+    computes; the counters do not depend on the sample order).  Raises
+    RuntimeError when some well has an empty ring, as the reference would."""
+    centres = np.arange(len(X), dtype=np.uint32)
+    offs, idx = rings_csr(X, Y, centres, levels)
+    _, counters = count_tile(planes, kinds, filt, centres, offs, idx, levels, edit_distance, use_hamming,
+                             want_per_target=False)
+    return counters

@@ -377,6 +377,78 @@ def test_error_paths(eng):
         eng.count(0, 1, [0], 2, False)                        # target well 200 on a 100-well tile
 
 
+# ------------------------------------------------------------ exhaustive mode --
+def _exhaustive_manifest():
+    with open(os.path.join(GOLDEN, "exhaustive", "manifest.json")) as fh:
+        return json.load(fh)
+
+
+@pytest.mark.parametrize("case", _exhaustive_manifest(), ids=lambda c: c["name"])
+def test_exhaustive_matches_reference_report(eng, oracle, case, tmp_path):
+    """wd_count_exhaustive (every well a target, neighbourhoods straight from the
+    stage-1 grid) prints what the unmodified reference printed for
+    prepare_cluster_indexes.py -n <all wells> + count_well_duplicates.py."""
+    R, CP = oracle
+    from well_duplicates_b200 import report
+    from well_duplicates_b200.reader import BCLReader
+    o = parse_count_args(case["args"])
+    _, xy = R.read_locs(locs_path(case["locs"], tmp_path))
+    eng.load_locs(xy)
+    rd = BCLReader(os.path.join(GOLDEN, "run_bcl"), engine=eng)
+    wanted = [c for s, e in o["ranges"] for c in range(s, e)]
+    rows = []
+    for k, t in enumerate(case["tiles"]):
+        plane_of = rd.get_tile(case["lane"], t).stage(k, wanted)
+        rows.append(eng.count_exhaustive(k, [plane_of[c] for c in wanted], o["levels"], o["edit"], o["hamming"]))
+    with open(os.path.join(GOLDEN, "exhaustive", case["name"] + ".stdout")) as fh:
+        want = fh.read()
+    assert report.format_report(case["lane"], xy.shape[0], case["tiles"], rows, o["levels"], verbose=True) == want
+
+
+@pytest.mark.parametrize("e,ham,levels", [(2, False, 5), (2, True, 5), (3, False, 2)])
+def test_exhaustive_medium_tile_vs_oracle(eng, oracle, e, ham, levels):
+    """A cropped tile (150 rows x 300 wells, 50 cycles), every well a target,
+    against the C oracle; also equal to the sampled path fed with all wells."""
+    R, CP = oracle
+    from well_duplicates_b200 import synth
+    rng = np.random.default_rng(31)
+    n, row_len, ncyc = 45000, 300, 50
+    X, Y = synth.hex_lattice(n, row_len)
+    td = synth.make_tile(rng, n, ncyc, row_len, dup_rate=0.1, shift_share=0.4, nocall_rate=0.003)
+    eng.load_locs(synth.xy_to_locs_floats(X, Y))
+    eng.tile_begin(0, n, ncyc)
+    eng.tile_put_filter(0, td.filt)
+    for c in range(ncyc):
+        eng.tile_put_bcl(0, c, td.planes[c])
+    order = list(range(ncyc))
+    got = eng.count_exhaustive(0, order, levels, e, ham)
+    want = CP.count_exhaustive(X, Y, [td.planes[c] for c in order], ["bcl"] * ncyc, td.filt, levels, e, ham)
+    assert np.array_equal(got, want)
+    centres = np.arange(n, dtype=np.uint32)
+    offs, idx = eng.ring_query(centres, levels)
+    eng.load_targets(centres, offs, idx, levels)
+    _, cnt = eng.count(0, 1, order, e, ham, mode=0, per_target=False)
+    assert np.array_equal(cnt[0], got)
+    assert got[2::5].sum() > 100
+
+
+def test_exhaustive_errors(eng, oracle):
+    R, CP = oracle
+    from well_duplicates_b200 import synth
+    # three wells far apart: every ring is empty -> the reference's RuntimeError
+    eng.load_locs(fx.sparse3())
+    eng.tile_begin(0, 3, 2)
+    eng.tile_put_filter(0, np.ones(3, np.uint8))
+    for c in range(2):
+        eng.tile_put_bcl(0, c, np.full(3, 5, np.uint8))
+    with pytest.raises(RuntimeError, match="Got no wells"):
+        eng.count_exhaustive(0, [0, 1])
+    # .locs and tile disagree on the number of wells
+    eng.load_locs(fx.hex_tiny())
+    with pytest.raises(AssertionError):
+        eng.count_exhaustive(0, [0, 1])
+
+
 # ------------------------------------------------------- full-size properties --
 @pytest.fixture(scope="module")
 def full_tile(eng):

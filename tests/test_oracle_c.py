@@ -92,3 +92,29 @@ def test_count_tile_matches_python_port(case):
         assert counters[0] == n_t
         assert counters[1::5].tolist() == wells and counters[2::5].tolist() == dups
         assert counters[3::5].tolist() == hits and counters[4::5].tolist() == acco and counters[5::5].tolist() == acci
+
+
+def _exhaustive_manifest():
+    with open(os.path.join(GOLDEN, "exhaustive", "manifest.json")) as fh:
+        return json.load(fh)
+
+
+@pytest.mark.parametrize("case", _exhaustive_manifest(), ids=lambda c: c["name"])
+def test_exhaustive_mode_matches_reference_report(case, tmp_path):
+    """Every well a target: the oracle's counters, printed, equal what the
+    unmodified reference printed (tests/golden/make_golden_exhaustive.py)."""
+    from well_duplicates_b200 import report
+    o = parse_count_args(case["args"])
+    _, xy = R.read_locs(locs_path(case["locs"], tmp_path))
+    X, Y = CP.locs_to_pixels(xy)
+    rows = []
+    for tile in case["tiles"]:
+        planes, kinds = [], []
+        for s, e in o["ranges"]:
+            p, kd, filt, n = R.load_tile_planes(os.path.join(GOLDEN, "run_bcl"), case["lane"], tile, s, e)
+            planes += p
+            kinds += kd
+        rows.append(CP.count_exhaustive(X, Y, planes, kinds, filt, o["levels"], o["edit"], o["hamming"]))
+    with open(os.path.join(GOLDEN, "exhaustive", case["name"] + ".stdout")) as fh:
+        want = fh.read()
+    assert report.format_report(case["lane"], len(X), case["tiles"], rows, o["levels"], verbose=True) == want

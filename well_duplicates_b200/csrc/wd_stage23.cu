@@ -16,6 +16,7 @@
 #include "wd_scan.cuh"
 #include "wd_seq.cuh"
 
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -230,7 +231,7 @@ gather_pack_kernel(const TileDesc *__restrict__ descs, const uint32_t *__restric
     const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
     if (s >= n_slots) return;
     const TileDesc d = descs[blockIdx.y];
-    const uint32_t well = __ldg(slot_well + s);
+    const uint32_t well = slot_well ? __ldg(slot_well + s) : s;     // null: every well in index order (exhaustive mode)
     PSeq<W> q;
     decode_well<W, ALL_BCL>(d, well, s_off, s_kind, len, q);
     const uint64_t meta = __ldg(d.filter + well) & 1u;
@@ -270,7 +271,8 @@ struct CountArgs {
     unsigned long long dup_cap;
     uint32_t t, n_slots;
     int levels, len, e, hamming;
-    int step0, step1;                // fused kernel: cycles per round (first, later); 4, 8 or 16
+    int step0, step1;                // fused kernel: cycles read per round (first, later), 1..16
+    int cchunk;                      // fused kernel: centre cycles decoded per warp-wide load (8, 16 or 32)
 };
 
 // Per-warp tallies -> per_target row and the CTA's shared counters.
@@ -387,11 +389,10 @@ compare_count_kernel(CountArgs a) {
 //    its prefix proves dist > e -- 96 % of unrelated reads after 6 symbols --
 //    so the later planes are touched only around real duplicates;
 //  * the centre is decoded by the whole warp (lane = cycle, three ballots turn
-//    the calls into bit-plane words), CENTRE_CHUNK cycles at a time and only as
+//    the calls into bit-plane words), 8-32 cycles at a time and only as
 //    far ahead as the programme needs (k = e/2 symbols past the ring wells): a
 //    target without duplicates never reads its centre beyond the first chunks.
 constexpr int FUSED_TPB = 64;    // targets per CTA; its 8 warps pull them from a shared counter
-constexpr int CENTRE_CHUNK = 16;
 
 // raw call (0 = no-call, else base = raw & 3) -> symbol 0..3, 4 = N
 __device__ __forceinline__ uint32_t call_symbol(uint32_t raw) { return raw == 0u ? 4u : (raw & 3u); }
@@ -509,13 +510,13 @@ fused_count_kernel(CountArgs a) {
                     while (known_c < need) {
                         const int q = known_c + lane;
                         uint32_t sym = 0u;
-                        if (lane < CENTRE_CHUNK && q < len)
+                        if (lane < a.cchunk && q < len)
                             sym = call_symbol(load_call<ALL_BCL>(d, centre, crank, s_off[q], ALL_BCL ? 0 : s_kind[q]));
                         const uint32_t glo = __ballot_sync(0xffffffffu, sym & 1u);
                         const uint32_t ghi = __ballot_sync(0xffffffffu, sym & 2u);
                         const uint32_t gnn = __ballot_sync(0xffffffffu, sym & 4u);
                         pseq_or_group<W>(c, known_c, glo, ghi, gnn);     // chunks never straddle a word
-                        known_c = min(len, known_c + CENTRE_CHUNK);
+                        known_c = min(len, known_c + a.cchunk);
                     }
                     // ---- ring wells: lane = well ---------------------------------------------
                     if (alive) {
@@ -783,6 +784,11 @@ int count_async(wd_ctx *ctx, int first_slot, int n_tiles, const int32_t *order, 
     const bool over_pcie = ctx->slots[first_slot].mapped != nullptr;
     a.step0 = over_pcie ? 4 : 8;
     a.step1 = over_pcie ? 1 : 2;
+    a.cchunk = over_pcie ? 8 : 16;
+    if (const char *cc = getenv("WELLDUP_CENTRE_CHUNK")) {
+        const int v = atoi(cc);
+        if (v == 8 || v == 16 || v == 32) a.cchunk = v;
+    }
     if (const char *sch = getenv("WELLDUP_STEPS")) {
         int s0 = 0, s1 = 0;
         if (sscanf(sch, "%d,%d", &s0, &s1) == 2 && s0 >= 1 && s0 <= 16 && s1 >= 1 && s1 <= 16) {
@@ -846,8 +852,187 @@ int publish_counters(wd_ctx *ctx, const int32_t *tile_row, const int32_t *lane_r
     return WD_OK;
 }
 
-int count_exhaustive(wd_ctx *, int, const int32_t *, int, int, uint32_t, uint32_t, int, int, int64_t *) {
-    WD_FAIL(WD_E_ARG, "wd_count_exhaustive: not built yet");
+// ============================================================================
+// Exhaustive mode (BASELINE config 3): every well is a target
+// ============================================================================
+// No target list exists: a warp takes one centre, walks the three grid rows of
+// stage 1 around it (contiguous runs of {x, y, well} records), keeps the wells
+// that fall into rings 1..levels under the reference's distance and index
+// window rules (prepare_cluster_indexes.py:19,52-67) in a per-warp list in
+// shared memory, and then compares the centre's packed words with theirs, 32
+// ring wells at a time.  Ring sizes (the LENGTH of the reference) fall out of
+// the same walk; a centre with an empty ring is the reference's RuntimeError
+// (:70-76) whether or not it passes the filter.
+constexpr int EXH_WARPS = 8;
+constexpr int EXH_CAP = 256;                       // ring wells kept per centre (a hex lattice has 90)
+__constant__ int c_exh_d2[6] = {1, 484, 1764, 3844, 6724, 10404};   // MAX_DISTS^2, as in wd_stage1.cu
+
+struct ExhArgs {
+    const int *px, *py;
+    const uint32_t *cell_start;
+    const int4 *cell_wells;
+    const uint8_t *filter;
+    const uint64_t *packed;              // [n][W][4]
+    unsigned long long *counters;        // [1 + 5 * levels]
+    uint32_t *first_empty;               // min over (centre * levels + level) with an empty ring
+    uint32_t *overflow;                  // a centre had more than EXH_CAP ring wells
+    uint32_t n;
+    int levels, len, e, hamming;
+    int min_x, min_y, grid_w, grid_h;
+    uint32_t wlo, whi;
+};
+
+template <int W>
+__global__ void __launch_bounds__(EXH_WARPS * 32)
+exhaustive_count_kernel(ExhArgs a) {
+    __shared__ uint32_t s_cnt[1 + 5 * 5];
+    __shared__ uint32_t s_list[EXH_WARPS][EXH_CAP];        // well | level << 29
+    for (int i = threadIdx.x; i < 1 + 5 * 5; i += blockDim.x) s_cnt[i] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    const uint32_t lt_mask = (1u << lane) - 1u;
+    const int L = a.levels;
+    const bool ham = a.hamming != 0;
+    // consecutive centres to consecutive warps: neighbouring wells share grid rows and packed words in L1/L2
+    for (uint32_t c = blockIdx.x * EXH_WARPS + warp; c < a.n; c += gridDim.x * EXH_WARPS) {
+        const int cx = __ldg(a.px + c), cy = __ldg(a.py + c);
+        const long long lo = (long long)c - (long long)a.wlo, hi = (long long)c + (long long)a.whi;
+        const int gx = (cx - a.min_x) >> 7, gy = (cy - a.min_y) >> 7;
+        uint32_t n_ring = 0;
+        uint32_t lens[5] = {0, 0, 0, 0, 0};
+        for (int yy = max(gy - 1, 0); yy <= min(gy + 1, a.grid_h - 1); ++yy) {
+            const int x0 = max(gx - 1, 0), x1 = min(gx + 1, a.grid_w - 1);
+            const uint32_t rs = __ldg(a.cell_start + (uint32_t)yy * a.grid_w + x0);
+            const uint32_t re = __ldg(a.cell_start + (uint32_t)yy * a.grid_w + x1 + 1);
+            for (uint32_t base = rs; base < re; base += 32) {
+                const uint32_t i = base + lane;
+                int lvl = -1;
+                uint32_t widx = 0;
+                if (i < re) {
+                    const int4 w = __ldg(a.cell_wells + i);
+                    const int dx = w.x - cx, dy = w.y - cy;
+                    widx = (uint32_t)w.z;
+                    if (abs(dx) <= 102 && abs(dy) <= 102 && (long long)w.z >= lo && (long long)w.z <= hi) {
+                        const int d2 = dx * dx + dy * dy;
+#pragma unroll
+                        for (int l = 0; l < 5; ++l)
+                            if (l < L && d2 > c_exh_d2[l] && d2 <= c_exh_d2[l + 1]) lvl = l;
+                    }
+                }
+                const uint32_t m = __ballot_sync(0xffffffffu, lvl >= 0);
+                if (lvl >= 0) {
+                    const uint32_t pos = n_ring + __popc(m & lt_mask);
+                    if (pos < EXH_CAP) s_list[warp][pos] = widx | ((uint32_t)lvl << 29);
+                }
+                n_ring += __popc(m);
+#pragma unroll
+                for (int l = 0; l < 5; ++l) lens[l] += __popc(__ballot_sync(0xffffffffu, lvl == l));
+            }
+        }
+        if (n_ring > EXH_CAP) {
+            if (lane == 0) atomicExch(a.overflow, 1u);
+            n_ring = EXH_CAP;
+        }
+#pragma unroll
+        for (int l = 0; l < 5; ++l)
+            if (l < L && lens[l] == 0 && lane == 0) atomicMin(a.first_empty, c * (uint32_t)L + l);
+        const bool valid = (__ldg(a.filter + c) & 1u) != 0;      // count_well_duplicates.py:236-237
+        __syncwarp();
+        if (valid) {
+            PSeq<W> cs;
+            load_packed<W>(a.packed + (size_t)c * (W * PACK_STRIDE), cs);
+            uint32_t dups[5] = {0, 0, 0, 0, 0};
+            for (uint32_t base = 0; base < n_ring; base += 32) {
+                const uint32_t i = base + lane;
+                bool dup = false;
+                int lvl = -1;
+                if (i < n_ring) {
+                    const uint32_t ent = s_list[warp][i];
+                    lvl = (int)(ent >> 29);
+                    PSeq<W> b;
+                    load_packed<W>(a.packed + (size_t)(ent & 0x1fffffffu) * (W * PACK_STRIDE), b);
+                    dup = is_duplicate<W>(cs, b, a.len, a.e, ham);
+                }
+#pragma unroll
+                for (int l = 0; l < 5; ++l) dups[l] += __popc(__ballot_sync(0xffffffffu, dup && lvl == l));
+            }
+            // the sums of output_writer (count_well_duplicates.py:77-106)
+            uint32_t hit_mask = 0;
+#pragma unroll
+            for (int l = 0; l < 5; ++l)
+                if (l < L && dups[l]) hit_mask |= 1u << l;
+            if (lane == 0) atomicAdd(&s_cnt[0], 1u);
+#pragma unroll
+            for (int l = 0; l < 5; ++l) {
+                if (l < L && lane == l) {
+                    uint32_t *cc = s_cnt + 1 + 5 * l;
+                    atomicAdd(cc + 0, lens[l]);
+                    if (dups[l]) {
+                        atomicAdd(cc + 1, dups[l]);
+                        atomicAdd(cc + 2, 1u);
+                    }
+                    if (hit_mask & ((2u << l) - 1u)) atomicAdd(cc + 3, 1u);
+                    if (hit_mask >> l) atomicAdd(cc + 4, 1u);
+                }
+            }
+        }
+        __syncwarp();
+    }
+    flush_counters(s_cnt, a.counters, 1 + 5 * L);
+}
+
+int count_exhaustive(wd_ctx *ctx, int slot, const int32_t *order, int seq_len, int levels, uint32_t wlo, uint32_t whi,
+                     int e, int hamming, int64_t *tile_counters) {
+    TileSlot &s = ctx->slots[slot];
+    if (levels < 1 || levels > 5) WD_FAIL(WD_E_ARG, "wd_count_exhaustive: levels must be 1..5 (MAX_DISTS defines 5 rings)");
+    if (ctx->n_locs == 0) WD_FAIL(WD_E_ARG, "wd_count_exhaustive: call wd_locs_load first");
+    if (ctx->n_locs != s.n)
+        WD_FAIL(WD_E_ASSERT, "wd_count_exhaustive: the .locs file holds %u wells, the tile %u", ctx->n_locs, s.n);
+    if (s.n >= (1u << 29)) WD_FAIL(WD_E_ARG, "wd_count_exhaustive: at most 2^29 wells per tile");
+    bool all_bcl, any_excl;
+    WD_TRY(prepare_order(ctx, slot, 1, order, seq_len, &all_bcl, &any_excl));
+    if (any_excl) WD_TRY(filter_rank(ctx, &slot, 1));
+    WD_TRY(upload_descs(ctx, slot, 1));
+    cudaStream_t st = ctx->stream;
+    const int words = words_for(seq_len);
+    const size_t width = 1 + 5 * (size_t)levels;
+    WD_TRY(ctx->x_packed.reserve((size_t)s.n * words * PACK_STRIDE * 8));
+    WD_TRY(ctx->x_counts.reserve(width * 8 + 8));
+    WD_CUDA(cudaMemsetAsync(ctx->x_counts.p, 0, width * 8 + 8, st));
+    uint32_t *flags = reinterpret_cast<uint32_t *>(ctx->x_counts.as<unsigned long long>() + width);
+    WD_CUDA(cudaMemsetAsync(flags, 0xff, 4, st));
+    // dense pass: every well packed once, in index order (coalesced plane reads)
+    launch_gather_any(ctx, words, all_bcl, ctx->descs.as<TileDesc>(), nullptr, s.n, 1, seq_len, ctx->x_packed.as<uint64_t>());
+    ExhArgs a;
+    a.px = ctx->px.as<int>(); a.py = ctx->py.as<int>();
+    a.cell_start = ctx->cell_start.as<uint32_t>(); a.cell_wells = ctx->cell_wells.as<int4>();
+    a.filter = s.mapped_filter ? s.mapped_filter : s.filter.as<uint8_t>();
+    a.packed = ctx->x_packed.as<uint64_t>();
+    a.counters = ctx->x_counts.as<unsigned long long>();
+    a.first_empty = flags; a.overflow = flags + 1;
+    a.n = s.n; a.levels = levels; a.len = seq_len; a.e = e; a.hamming = hamming;
+    a.min_x = ctx->min_x; a.min_y = ctx->min_y; a.grid_w = ctx->grid_w; a.grid_h = ctx->grid_h;
+    a.wlo = wlo; a.whi = whi;
+    const unsigned blocks = (unsigned)std::min<size_t>(((size_t)s.n + EXH_WARPS - 1) / EXH_WARPS, (size_t)ctx->sm_count * 8);
+    switch (words) {
+        case 1: exhaustive_count_kernel<1><<<blocks, EXH_WARPS * 32, 0, st>>>(a); break;
+        case 2: exhaustive_count_kernel<2><<<blocks, EXH_WARPS * 32, 0, st>>>(a); break;
+        case 4: exhaustive_count_kernel<4><<<blocks, EXH_WARPS * 32, 0, st>>>(a); break;
+        case 8: exhaustive_count_kernel<8><<<blocks, EXH_WARPS * 32, 0, st>>>(a); break;
+        default: exhaustive_count_kernel<16><<<blocks, EXH_WARPS * 32, 0, st>>>(a); break;
+    }
+    ctx->launches++;
+    WD_CUDA(cudaGetLastError());
+    std::vector<unsigned long long> h(width + 1);
+    WD_CUDA(cudaMemcpyAsync(h.data(), ctx->x_counts.p, (width + 1) * 8, cudaMemcpyDeviceToHost, st));
+    WD_CUDA(cudaStreamSynchronize(st));
+    uint32_t fl[2];
+    memcpy(fl, &h[width], 8);
+    if (fl[1]) WD_FAIL(WD_E_ARG, "wd_count_exhaustive: a well has more than %d ring wells; the grid is denser than supported", EXH_CAP);
+    if (fl[0] != UINT32_MAX)
+        WD_FAIL(WD_E_RUNTIME, "Got no wells for cluster %u level %u", fl[0] / levels, fl[0] % levels);
+    for (size_t i = 0; i < width; ++i) tile_counters[i] = (int64_t)h[i];
+    return WD_OK;
 }
 
 }  // namespace wd
