@@ -87,3 +87,27 @@ extern "C" int seq_prefix_dp(const uint8_t *a, const uint8_t *b, int len, int wo
     }
     return -1;
 }
+
+template <int W>
+static int head32(const uint8_t *a, const uint8_t *b, int len, int e, int ham) {
+    wd::PSeq<W> pa, pb;
+    wd::pseq_clear(pa);
+    wd::pseq_clear(pb);
+    for (int i = 0; i < len; ++i) {
+        wd::pseq_set<W>(pa, i, a[i]);
+        wd::pseq_set<W>(pb, i, b[i]);
+    }
+    return wd::head32_rejects<W>(pa, pb, len, e, ham != 0 || e < 2) ? 1 : 0;
+}
+
+// 1 when the 32-symbol pre-filter of exhaustive mode rejects the pair
+extern "C" int seq_head32_rejects(const uint8_t *a, const uint8_t *b, int len, int words, int e, int ham) {
+    switch (words) {
+        case 1: return head32<1>(a, b, len, e, ham);
+        case 2: return head32<2>(a, b, len, e, ham);
+        case 4: return head32<4>(a, b, len, e, ham);
+        case 8: return head32<8>(a, b, len, e, ham);
+        case 16: return head32<16>(a, b, len, e, ham);
+    }
+    return -1;
+}

@@ -21,6 +21,7 @@ def harness(tmp_path_factory):
     lib = ctypes.CDLL(so)
     lib.seq_check.argtypes = [ctypes.c_char_p, ctypes.c_char_p] + [ctypes.c_int] * 4 + [ctypes.POINTER(ctypes.c_int)] * 3
     lib.seq_first_reject.argtypes = [ctypes.c_char_p, ctypes.c_char_p] + [ctypes.c_int] * 4
+    lib.seq_head32_rejects.argtypes = [ctypes.c_char_p, ctypes.c_char_p] + [ctypes.c_int] * 4
     lib.seq_prefix_dp.argtypes = [ctypes.c_char_p, ctypes.c_char_p] + [ctypes.c_int] * 4 + [ctypes.POINTER(ctypes.c_int)]
     return lib
 
@@ -157,3 +158,31 @@ def test_incremental_prefix_dp(harness, lengths):
             assert (got[n] <= e) == (lev <= e)
             if lev <= e:
                 assert all(got[p] <= e for p in range(1, n + 1)), "prefix test rejected a true duplicate"
+
+
+@pytest.mark.parametrize("lengths", [(1, 31), (32, 64), (65, 200)])
+def test_head32_prefilter_is_safe_and_useful(harness, lengths):
+    """The 32-symbol pre-filter of exhaustive mode never rejects a pair within
+    distance e, and it does reject nearly all unrelated pairs."""
+    rng = np.random.default_rng(200 + lengths[0])
+    fired, unrelated = 0, 0
+    for _ in range(600):
+        n = int(rng.integers(lengths[0], lengths[1] + 1))
+        a = [int(v) for v in rng.integers(0, 5, n)]
+        related = rng.random() < 0.6
+        b = mutate(rng, a) if related else [int(v) for v in rng.integers(0, 4, n)]
+        sa = "".join("ACGTN"[v] for v in a)
+        sb = "".join("ACGTN"[v] for v in b)
+        lev, hd = R.levenshtein(sa, sb), R.hamming(sa, sb)
+        w = words_for(n)
+        for e in (0, 1, 2, 3, 5, 8, 31):
+            if e >= n:
+                continue
+            for ham, dist in ((0, lev), (1, hd)):
+                if harness.seq_head32_rejects(bytes(a), bytes(b), n, w, e, ham):
+                    assert dist > e, (sa, sb, e, ham)
+        if not related and n >= 32:
+            unrelated += 1
+            fired += harness.seq_head32_rejects(bytes(a), bytes(b), n, w, 2, 0)
+    if unrelated:
+        assert fired > 0.97 * unrelated

@@ -42,6 +42,15 @@ struct DevBuf {
     T *as() const { return reinterpret_cast<T *>(p); }
 };
 
+// ---- stage-1 grid ------------------------------------------------------------------
+// Cells are 32 px wide and 128 px tall.  128 >= the largest ring radius (102 px), so three
+// grid rows cover every ring; inside a grid row the cells are contiguous in memory, so the
+// wells with |dx| <= 102 are ONE run of records (cells (cx-102)>>5 .. (cx+102)>>5, 7-8 narrow
+// cells, ~250 px instead of the 384 px three square cells would span).
+constexpr int CELL_SHIFT_X = 5;
+constexpr int CELL_SHIFT_Y = 7;
+constexpr int RING_RADIUS = 102;                    // MAX_DISTS[-1], prepare_cluster_indexes.py:19
+
 // ---- one tile's planes in HBM ---------------------------------------------------
 struct TileDesc {                 // what the kernels see (array in device memory)
     const uint8_t *planes;        // n_planes x stride bytes

@@ -325,6 +325,33 @@ WD_HD int pdp_band_min(const PrefixDP<W> &s, int len, int p, int k) {
     return best;
 }
 
+// cheap necessary condition for dist <= e on the first 32 symbols only (32-bit
+// ops): the running mismatch count for Hamming-like tests, the shifted-Hamming
+// bound of wd_seq.cuh restricted to a 32-symbol prefix of b otherwise.  99.9 %
+// of the ring wells are unrelated reads and stop here.
+template <int W>
+WD_HD bool head32_rejects(const PSeq<W> &a, const PSeq<W> &b, int len, int e, bool ham_like) {
+    const int n = len < 32 ? len : 32;
+    const uint32_t m = n >= 32 ? ~0u : ((1u << n) - 1u);
+    const uint32_t alo = (uint32_t)a.lo[0], ahi = (uint32_t)a.hi[0], ann = (uint32_t)a.nn[0];
+    const uint32_t blo = (uint32_t)b.lo[0], bhi = (uint32_t)b.hi[0], bnn = (uint32_t)b.nn[0];
+    uint32_t all = ((alo ^ blo) | (ahi ^ bhi) | (ann ^ bnn)) & m;
+    if (!ham_like) {
+        const int k = e >> 1;
+        if (k >= 16) return false;
+        // a[j + d] for j < 32 needs bits of a up to 32 + k: take them from the 64-bit word
+        for (int d = 1; d <= k; ++d) {
+            const uint32_t ulo = (uint32_t)(a.lo[0] >> d), uhi = (uint32_t)(a.hi[0] >> d), unn = (uint32_t)(a.nn[0] >> d);
+            uint32_t up = (ulo ^ blo) | (uhi ^ bhi) | (unn ^ bnn);
+            const int cut = len - d;                                   // partner j + d must be < len
+            if (cut < 32) up |= cut <= 0 ? ~0u : ~((1u << cut) - 1u);
+            const uint32_t dn = (((alo << d) ^ blo) | ((ahi << d) ^ bhi) | ((ann << d) ^ bnn)) | ((1u << d) - 1u);
+            all &= up & dn;
+        }
+    }
+    return popc32(all & m) > e;
+}
+
 // dist(a, b) <= e under the reference's chosen metric.
 template <int W>
 WD_HD bool is_duplicate(const PSeq<W> &a, const PSeq<W> &b, int len, int e, bool use_hamming) {

@@ -1,9 +1,9 @@
 // Stage 1 -- hex-lattice neighbourhood construction (K0, K1, K2).
 //
 // Replaces the per-target linear scan of prepare_cluster_indexes.py:38-78 by a
-// uniform-grid spatial hash: wells are binned into 128-px cells (>= the largest
-// ring radius, 102 px, so a 3x3 block of cells covers every ring), and each
-// target is served by one warp that tests only the wells of those nine cells.
+// uniform-grid spatial hash: wells are binned into cells 32 px wide and 128 px
+// tall (wd_common.cuh), and each target is served by one warp that tests only
+// the wells of three runs of cells, one per grid row around the centre.
 // The membership rule is the reference's, restated in integers:
 //   MAX[l] < sqrt(dx^2+dy^2) <= MAX[l+1]   <=>   MAX[l]^2 < dx^2+dy^2 <= MAX[l+1]^2
 // (exact: sqrt is correctly rounded and the thresholds are integers), together
@@ -15,10 +15,8 @@
 
 namespace wd {
 
-constexpr int CELL_SHIFT = 7;                       // 128-px cells
 constexpr int RING_LEVELS = 5;                      // len(MAX_DISTS) - 1, prepare_cluster_indexes.py:19
 __constant__ int c_ring_d2[RING_LEVELS + 1] = {1, 484, 1764, 3844, 6724, 10404};   // MAX_DISTS^2
-constexpr int RING_RADIUS = 102;
 
 // ---- K0: .locs floats -> integer pixels -------------------------------------------
 // x = int(f * 10.0 + 1000.5) evaluated in float64 with truncation toward zero
@@ -59,7 +57,7 @@ locs_to_pixels_kernel(const float2 *__restrict__ xy, uint32_t n, int *__restrict
 
 // ---- K1: uniform grid (histogram -> scan -> scatter) -------------------------------------
 __device__ __forceinline__ uint32_t cell_of(int x, int y, int min_x, int min_y, int grid_w) {
-    return (uint32_t)((y - min_y) >> CELL_SHIFT) * (uint32_t)grid_w + (uint32_t)((x - min_x) >> CELL_SHIFT);
+    return (uint32_t)((y - min_y) >> CELL_SHIFT_Y) * (uint32_t)grid_w + (uint32_t)((x - min_x) >> CELL_SHIFT_X);
 }
 
 __global__ void __launch_bounds__(256)
@@ -107,14 +105,15 @@ ring_query_kernel(RingArgs a, uint32_t *__restrict__ counts, uint32_t *__restric
     const int cx = a.px[c], cy = a.py[c];
     const long long lo = (long long)c - (long long)a.wlo;
     const long long hi = (long long)c + (long long)a.whi;
-    const int gx = (cx - a.min_x) >> CELL_SHIFT, gy = (cy - a.min_y) >> CELL_SHIFT;
+    const int gy = (cy - a.min_y) >> CELL_SHIFT_Y;
+    const int x0 = max(cx - RING_RADIUS - a.min_x, 0) >> CELL_SHIFT_X;
+    const int x1 = min((cx + RING_RADIUS - a.min_x) >> CELL_SHIFT_X, a.grid_w - 1);
     uint32_t run[RING_LEVELS];
 #pragma unroll
     for (int l = 0; l < RING_LEVELS; ++l) run[l] = 0;
     const uint32_t lt_mask = (1u << lane) - 1u;
 
     for (int yy = max(gy - 1, 0); yy <= min(gy + 1, a.grid_h - 1); ++yy) {
-        const int x0 = max(gx - 1, 0), x1 = min(gx + 1, a.grid_w - 1);
         // the cells of one grid row are contiguous in cell_wells
         const uint32_t s = a.cell_start[(uint32_t)yy * a.grid_w + x0];
         const uint32_t e = a.cell_start[(uint32_t)yy * a.grid_w + x1 + 1];
@@ -201,8 +200,8 @@ int locs_load(wd_ctx *ctx, const float *xy, uint32_t n) {
     if (h[4]) WD_FAIL(WD_E_ARG, "wd_locs_load: non-finite or out-of-range coordinate in .locs");
     ctx->min_x = h[0];
     ctx->min_y = h[1];
-    const long long gw = (((long long)h[2] - h[0]) >> CELL_SHIFT) + 1;
-    const long long gh = (((long long)h[3] - h[1]) >> CELL_SHIFT) + 1;
+    const long long gw = (((long long)h[2] - h[0]) >> CELL_SHIFT_X) + 1;
+    const long long gh = (((long long)h[3] - h[1]) >> CELL_SHIFT_Y) + 1;
     if (gw * gh > (1ll << 26))
         WD_FAIL(WD_E_ARG, "wd_locs_load: coordinate bounding box %lld x %lld cells is too large", gw, gh);
     ctx->grid_w = (int)gw;

@@ -883,7 +883,7 @@ struct ExhArgs {
 };
 
 template <int W>
-__global__ void __launch_bounds__(EXH_WARPS * 32)
+__global__ void __launch_bounds__(EXH_WARPS * 32, W == 1 ? 5 : 1)
 exhaustive_count_kernel(ExhArgs a) {
     __shared__ uint32_t s_cnt[1 + 5 * 5];
     __shared__ uint32_t s_list[EXH_WARPS][EXH_CAP];        // well | level << 29
@@ -893,69 +893,79 @@ exhaustive_count_kernel(ExhArgs a) {
     const uint32_t lt_mask = (1u << lane) - 1u;
     const int L = a.levels;
     const bool ham = a.hamming != 0;
+    const bool ham_like = ham || a.e < 2;
+    const bool prefilter = a.e >= 0 && a.e < a.len;
+    const int d2_max = c_exh_d2[L];
     // consecutive centres to consecutive warps: neighbouring wells share grid rows and packed words in L1/L2
     for (uint32_t c = blockIdx.x * EXH_WARPS + warp; c < a.n; c += gridDim.x * EXH_WARPS) {
         const int cx = __ldg(a.px + c), cy = __ldg(a.py + c);
-        const long long lo = (long long)c - (long long)a.wlo, hi = (long long)c + (long long)a.whi;
-        const int gx = (cx - a.min_x) >> 7, gy = (cy - a.min_y) >> 7;
+        // index window [c - wlo, c + whi] (wells are < 2^29, the bounds are clamped to that range)
+        const int lo = (int)max((long long)c - (long long)a.wlo, 0ll);
+        const int hi = (int)min((long long)c + (long long)a.whi, (long long)0x7fffffff);
+        const int x0 = max(cx - RING_RADIUS - a.min_x, 0) >> CELL_SHIFT_X;
+        const int x1 = min((cx + RING_RADIUS - a.min_x) >> CELL_SHIFT_X, a.grid_w - 1);
+        const int y0 = max(cy - RING_RADIUS - a.min_y, 0) >> CELL_SHIFT_Y;       // two or three grid rows
+        const int y1 = min((cy + RING_RADIUS - a.min_y) >> CELL_SHIFT_Y, a.grid_h - 1);
         uint32_t n_ring = 0;
-        uint32_t lens[5] = {0, 0, 0, 0, 0};
-        for (int yy = max(gy - 1, 0); yy <= min(gy + 1, a.grid_h - 1); ++yy) {
-            const int x0 = max(gx - 1, 0), x1 = min(gx + 1, a.grid_w - 1);
+        for (int yy = y0; yy <= y1; ++yy) {
             const uint32_t rs = __ldg(a.cell_start + (uint32_t)yy * a.grid_w + x0);
             const uint32_t re = __ldg(a.cell_start + (uint32_t)yy * a.grid_w + x1 + 1);
             for (uint32_t base = rs; base < re; base += 32) {
                 const uint32_t i = base + lane;
-                int lvl = -1;
-                uint32_t widx = 0;
+                bool in = false;
+                uint32_t ent = 0;
                 if (i < re) {
                     const int4 w = __ldg(a.cell_wells + i);
-                    const int dx = w.x - cx, dy = w.y - cy;
-                    widx = (uint32_t)w.z;
-                    if (abs(dx) <= 102 && abs(dy) <= 102 && (long long)w.z >= lo && (long long)w.z <= hi) {
-                        const int d2 = dx * dx + dy * dy;
-#pragma unroll
-                        for (int l = 0; l < 5; ++l)
-                            if (l < L && d2 > c_exh_d2[l] && d2 <= c_exh_d2[l + 1]) lvl = l;
-                    }
+                    const int dx = w.x - cx, dy = w.y - cy;         // |dx| < 256 + 32, |dy| < 256: no overflow
+                    const int d2 = dx * dx + dy * dy;
+                    // MAX[l] < dist <= MAX[l+1]  <=>  MAX[l]^2 < d2 <= MAX[l+1]^2
+                    const int lvl = (d2 > 484) + (d2 > 1764) + (d2 > 3844) + (d2 > 6724);
+                    in = d2 > 1 && d2 <= d2_max && w.z >= lo && w.z <= hi;
+                    ent = (uint32_t)w.z | ((uint32_t)lvl << 29);
                 }
-                const uint32_t m = __ballot_sync(0xffffffffu, lvl >= 0);
-                if (lvl >= 0) {
+                const uint32_t m = __ballot_sync(0xffffffffu, in);
+                if (in) {
                     const uint32_t pos = n_ring + __popc(m & lt_mask);
-                    if (pos < EXH_CAP) s_list[warp][pos] = widx | ((uint32_t)lvl << 29);
+                    if (pos < EXH_CAP) s_list[warp][pos] = ent;
                 }
                 n_ring += __popc(m);
-#pragma unroll
-                for (int l = 0; l < 5; ++l) lens[l] += __popc(__ballot_sync(0xffffffffu, lvl == l));
             }
         }
         if (n_ring > EXH_CAP) {
             if (lane == 0) atomicExch(a.overflow, 1u);
             n_ring = EXH_CAP;
         }
+        const bool valid = (__ldg(a.filter + c) & 1u) != 0;      // count_well_duplicates.py:236-237
+        __syncwarp();
+        PSeq<W> cs;
+        if (valid) load_packed<W>(a.packed + (size_t)c * (W * PACK_STRIDE), cs);
+        uint32_t dups[5] = {0, 0, 0, 0, 0};
+        uint32_t lens[5] = {0, 0, 0, 0, 0};
+        for (uint32_t base = 0; base < n_ring; base += 32) {
+            const uint32_t i = base + lane;
+            bool dup = false;
+            int lvl = -1;
+            if (i < n_ring) {
+                const uint32_t ent = s_list[warp][i];
+                lvl = (int)(ent >> 29);
+                if (valid) {
+                    PSeq<W> b;
+                    load_packed<W>(a.packed + (size_t)(ent & 0x1fffffffu) * (W * PACK_STRIDE), b);
+                    if (!(prefilter && head32_rejects<W>(cs, b, a.len, a.e, ham_like)))
+                        dup = is_duplicate<W>(cs, b, a.len, a.e, ham);
+                }
+            }
+#pragma unroll
+            for (int l = 0; l < 5; ++l) {
+                lens[l] += __popc(__ballot_sync(0xffffffffu, lvl == l));
+                dups[l] += __popc(__ballot_sync(0xffffffffu, dup && lvl == l));
+            }
+        }
+        // a ring without wells is the reference's RuntimeError, pass-filter centre or not
 #pragma unroll
         for (int l = 0; l < 5; ++l)
             if (l < L && lens[l] == 0 && lane == 0) atomicMin(a.first_empty, c * (uint32_t)L + l);
-        const bool valid = (__ldg(a.filter + c) & 1u) != 0;      // count_well_duplicates.py:236-237
-        __syncwarp();
         if (valid) {
-            PSeq<W> cs;
-            load_packed<W>(a.packed + (size_t)c * (W * PACK_STRIDE), cs);
-            uint32_t dups[5] = {0, 0, 0, 0, 0};
-            for (uint32_t base = 0; base < n_ring; base += 32) {
-                const uint32_t i = base + lane;
-                bool dup = false;
-                int lvl = -1;
-                if (i < n_ring) {
-                    const uint32_t ent = s_list[warp][i];
-                    lvl = (int)(ent >> 29);
-                    PSeq<W> b;
-                    load_packed<W>(a.packed + (size_t)(ent & 0x1fffffffu) * (W * PACK_STRIDE), b);
-                    dup = is_duplicate<W>(cs, b, a.len, a.e, ham);
-                }
-#pragma unroll
-                for (int l = 0; l < 5; ++l) dups[l] += __popc(__ballot_sync(0xffffffffu, dup && lvl == l));
-            }
             // the sums of output_writer (count_well_duplicates.py:77-106)
             uint32_t hit_mask = 0;
 #pragma unroll
