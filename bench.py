@@ -8,9 +8,13 @@ lane of 96 tiles x 4 309 650 wells, 2500 sampled targets out to ring 5, a
 50-cycle substring from BCL byte planes, default (Levenshtein, e = 2) compare.
 A step is one pass of the hot path (fused gather-decode + compare + counter
 reduction, then the lane-counter all-reduce when N > 1) over all of the rank's
-tiles.  `value` has the planes resident in HBM; `e2e` pushes every plane from
-pinned host memory through the C ABI inside the timed region and reads the
-counters back.  Gunzip is outside both (BASELINE.json north_star).
+tiles.  `value` has the planes resident in HBM.  `e2e` starts every step from
+planes in pinned HOST memory and ends with the counters on the host, through
+the C ABI: the product's staging (wd_tile_map_host) leaves the planes where the
+inflate step wrote them and the kernel pulls the 32-byte sectors it needs across
+PCIe; `e2e_staged` is the same step with every plane copied to HBM first
+(wd_tile_put_bcl), for comparison.  Gunzip is outside all of them
+(BASELINE.json north_star).
 
 `--impl reference` times the CPU restatement of the reference (oracle/, C port,
 all host threads) on a bounded sample of the same workload.
@@ -52,12 +56,14 @@ def parse():
                     help="distinct synthetic tiles kept in pinned host memory (reused round-robin for the tile slots)")
     ap.add_argument("--mode", type=int, default=0, help="0 fused kernel, 1 two-pass kernels")
     ap.add_argument("--e2e-steps", type=int, default=2)
-    ap.add_argument("--e2e-mode", default="staged", choices=["staged", "zerocopy", "both"],
+    ap.add_argument("--e2e-mode", default="both", choices=["staged", "zerocopy", "both"],
                     help="staged: every plane copied to HBM through wd_tile_put_bcl; zerocopy: planes stay in pinned "
                          "host memory (wd_tile_map_host) and the kernel pulls the sectors it needs over PCIe")
     ap.add_argument("--cpu-tiles", type=int, default=0, help="tiles in the cpu_baseline sample (0 = 24 per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--hamming", action="store_true")
+    ap.add_argument("--zc-blocks", type=int, default=0,
+                    help="distinct pinned host blocks for the zero-copy e2e (0 = one per tile slot if the host can pin them)")
     ap.add_argument("--sweep-steps", default="", help="early-exit schedules to time in this process, e.g. '8,4;8,2;6,2' "
                                                       "(sets WELLDUP_STEPS; resident planes, and zero-copy when --e2e-mode asks)")
     ap.add_argument("--l2-fetch", type=int, default=0, help="override cudaLimitMaxL2FetchGranularity (32/64/128)")
@@ -151,11 +157,12 @@ def load_peaks():
     return 6650.0, "fallback"
 
 
-def load_traffic(mode):
+def load_traffic(key):
+    """Per-launch byte counts taken from committed ncu captures (profiles/traffic.json)."""
     p = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(p):
         with open(p) as fh:
-            return json.load(fh).get("fused" if mode == 0 else "two_pass")
+            return json.load(fh).get(key)
     return None
 
 
@@ -343,14 +350,18 @@ def main():
         sweep = {}
         schedules = [x for x in args.sweep_steps.split(";") if x]
         def set_schedule(sch):
-            # "first,later" or "first,later,centre_chunk"; None restores the library's defaults
-            os.environ.pop("WELLDUP_STEPS", None)
-            os.environ.pop("WELLDUP_CENTRE_CHUNK", None)
-            if sch:
-                f = sch.split(",")
-                os.environ["WELLDUP_STEPS"] = ",".join(f[:2])
-                if len(f) > 2:
-                    os.environ["WELLDUP_CENTRE_CHUNK"] = f[2]
+            # "first,later[,centre_chunk]" and/or "NAME=value" tunables, space separated; None restores the defaults
+            for k in [k for k in os.environ if k.startswith("WELLDUP_")]:
+                os.environ.pop(k)
+            for item in (sch or "").split():
+                if "=" in item:
+                    k, v = item.split("=", 1)
+                    os.environ["WELLDUP_" + k] = v
+                else:
+                    f = item.split(",")
+                    os.environ["WELLDUP_STEPS"] = ",".join(f[:2])
+                    if len(f) > 2:
+                        os.environ["WELLDUP_CENTRE_CHUNK"] = f[2]
 
         for sch in schedules:
             set_schedule(sch)
@@ -361,17 +372,27 @@ def main():
         # ---- e2e, zero-copy flavour: planes stay in pinned host memory ------------------
         zc_ms = None
         if args.e2e_steps > 0 and args.e2e_mode in ("zerocopy", "both"):
-            # one distinct pinned block per tile slot, so that no slot can hit another slot's lines in L2
-            zc = list(pins) + [PinnedArray((N_CYCLES, N_WELLS)) for _ in range(n_tiles - D)]
-            zc_filt = list(filt_pins) + [PinnedArray((N_WELLS,)) for _ in range(n_tiles - D)]
+            # one distinct pinned block per tile slot, so that no slot can be served from lines another
+            # slot brought into L2 -- unless the host cannot pin that much (then the D blocks are shared)
+            n_zc = n_tiles if args.zc_blocks <= 0 else max(D, min(n_tiles, args.zc_blocks))
+            local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
+            need = (n_zc - D) * (N_CYCLES + 1) * N_WELLS * local_world
+            try:
+                import psutil
+                if args.zc_blocks <= 0 and psutil.virtual_memory().available < 1.25 * need + (8 << 30):
+                    n_zc = D
+            except ImportError:
+                pass
+            zc = list(pins) + [PinnedArray((N_CYCLES, N_WELLS)) for _ in range(n_zc - D)]
+            zc_filt = list(filt_pins) + [PinnedArray((N_WELLS,)) for _ in range(n_zc - D)]
             with ThreadPoolExecutor(max_workers=8) as pool:
-                list(pool.map(lambda s: np.copyto(zc[s].array, pins[s % D].array), range(D, n_tiles)))
-            for s in range(D, n_tiles):
+                list(pool.map(lambda s: np.copyto(zc[s].array, pins[s % D].array), range(D, n_zc)))
+            for s in range(D, n_zc):
                 zc_filt[s].array[:] = filt_pins[s % D].array
 
             def map_tiles():
                 for s in range(n_tiles):
-                    eng.tile_map_host(s, N_WELLS, zc[s].array, pinned_filter=zc_filt[s].array)
+                    eng.tile_map_host(s, N_WELLS, zc[s % n_zc].array, pinned_filter=zc_filt[s % n_zc].array)
 
             map_tiles()
             zc_counters = step(True)
@@ -386,6 +407,7 @@ def main():
             barrier()
             zc_ms = ev4.elapsed_time(ev5) / args.e2e_steps
             d2h_per_step = int(res.size * 8)
+            zc_dma_bytes = eng.last_count_h2d_bytes()
 
             def zc_step():
                 map_tiles()
@@ -435,7 +457,7 @@ def main():
         per_tile = [algorithmic_bytes(centres, offs, idx, tds[k].filt, fused=(args.mode == 0)) for k in range(D)]
         alg_bytes = sum(per_tile[s % D][0] for s in range(n_tiles))
         achieved = alg_bytes / (ms_per_step / 1e3) / 1e9
-        traffic = load_traffic(args.mode)
+        traffic = load_traffic("fused" if args.mode == 0 else "two_pass")
         line = {
             "metric": METRIC, "value": value, "unit": "targets/s", "n_gpus": world, "steps": args.steps,
             "warmup": max(3, args.warmup), "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak",
@@ -450,18 +472,34 @@ def main():
                          "distinct_32B_sectors_per_plane_per_tile": int(np.mean([p[1] for p in per_tile])),
                          "note": "duration = CUDA events around %d launches on the launching stream; at N>1 it also "
                                  "covers the publish kernel and the all-reduce" % args.steps},
-            "e2e": None if e2e_ms is None else {
-                "value": targets_per_step / (e2e_ms / 1e3), "unit": "targets/s", "ms_per_step": e2e_ms,
-                "h2d_bytes_per_step": int(h2d_per_step), "d2h_bytes_per_step": d2h_per_step,
-                "h2d_gb_per_s": h2d_per_step / (e2e_ms / 1e3) / 1e9},
         }
+        staged = None if e2e_ms is None else {
+            "value": targets_per_step / (e2e_ms / 1e3), "unit": "targets/s", "ms_per_step": e2e_ms,
+            "staging": "wd_tile_put_bcl: every plane copied from pinned host memory to HBM, then counted",
+            "h2d_bytes_per_step": int(h2d_per_step), "d2h_bytes_per_step": d2h_per_step,
+            "h2d_gb_per_s": h2d_per_step / (e2e_ms / 1e3) / 1e9}
+        if zc_ms is not None:
+            pulled = load_traffic("zero_copy_pcie_read_bytes")
+            line["e2e"] = {
+                "value": targets_per_step / (zc_ms / 1e3), "unit": "targets/s", "ms_per_step": zc_ms,
+                "staging": "wd_tile_map_host: planes and filters stay in pinned host memory (%.1f GB per step and GPU); "
+                           "wd_count copies the planes of the first 2 compared cycles to HBM by DMA, tile group after "
+                           "tile group, while the counting kernel reads the sectors it needs of the later planes "
+                           "across PCIe" % (n_tiles * (N_CYCLES + 1) * N_WELLS / 1e9),
+                "h2d_bytes_per_step": int(zc_dma_bytes + (0 if pulled is None else pulled * n_tiles / TILES_PER_LANE)),
+                "h2d_dma_bytes_per_step": int(zc_dma_bytes),
+                "h2d_pulled_bytes_per_step": None if pulled is None else int(pulled * n_tiles / TILES_PER_LANE),
+                "h2d_bytes_note": "DMA bytes are counted by the library; pulled bytes = pcie__read_bytes of the step's "
+                                  "kernels in the committed ncu capture (profiles/traffic.json)",
+                "host_bytes_mapped_per_step": int(n_tiles * (N_CYCLES + 1) * N_WELLS),
+                "distinct_host_blocks": n_zc,
+                "d2h_bytes_per_step": d2h_per_step, "counters_equal_staged_run": zc_ok}
+            if staged is not None:
+                line["e2e_staged"] = staged
+        else:
+            line["e2e"] = staged
         if sweep:
             line["sweep_steps"] = sweep
-        if zc_ms is not None:
-            line["e2e_zero_copy"] = {
-                "value": targets_per_step / (zc_ms / 1e3), "unit": "targets/s", "ms_per_step": zc_ms,
-                "counters_equal_staged": zc_ok, "host_bytes_mapped_per_step": int(n_tiles * N_CYCLES * N_WELLS),
-                "h2d_copy_bytes_per_step": 0, "d2h_bytes_per_step": d2h_per_step}
         if not args.no_cpu_baseline and world == 1:
             cores = os.cpu_count() or 1
             n_cpu = args.cpu_tiles or 24 * cores

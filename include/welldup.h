@@ -78,6 +78,9 @@ WD_API int wd_host_free(void *p);
  * cudaLimitMaxL2FetchGranularity).  The scattered plane gathers use a few bytes
  * per 32-byte sector, so wd_create() asks for 32; *previous receives the old value. */
 WD_API int wd_set_l2_fetch_granularity(wd_ctx *ctx, int bytes, int *previous);
+/* Bytes the last wd_count / wd_count_async copied from host-mapped tiles to HBM by DMA (the planes
+ * of the first compared positions, see wd_tile_map_host); 0 for staged tiles. */
+WD_API int wd_last_count_h2d_bytes(wd_ctx *ctx, uint64_t *out);
 /* Number of kernel launches issued by this context so far (bench.py gpu_launches). */
 WD_API int wd_launch_count(wd_ctx *ctx, uint64_t *out);
 
@@ -123,10 +126,12 @@ WD_API int wd_tile_put_cbcl(wd_ctx *ctx, int tile_slot, int plane, const uint8_t
                      uint32_t usize, uint32_t n_block, int excluded);
 /* Zero-copy staging, instead of wd_tile_begin + wd_tile_put_bcl/_cbcl: the
  * tile's inflated planes stay where the host put them -- planes[p * stride_bytes]
- * in page-locked memory from wd_host_alloc() -- and the counting kernels pull
- * only the 32-byte sectors they touch across PCIe (a few per cent of a sampled
- * tile) instead of the whole 215 MB the per-cycle slurp of
- * bcl_direct_reader.py:333-345 moves.  kinds[p] is a WD_PLANE_* (NULL = all
+ * in page-locked memory from wd_host_alloc().  wd_count then copies only the
+ * planes of the first two compared positions to HBM (DMA, overlapped tile
+ * group by tile group with the kernels) and the counting kernel pulls the
+ * 32-byte sectors it needs of the later planes straight across PCIe -- a few
+ * per cent of a sampled tile instead of the whole 215 MB the per-cycle slurp
+ * of bcl_direct_reader.py:333-345 moves.  kinds[p] is a WD_PLANE_* (NULL = all
  * BCL), n_block[p] the cluster count of a CBCL block (NULL = n_clusters).  The
  * memory must stay unchanged until the results of the last wd_count that uses
  * the slot have been fetched.  filter (n_clusters bytes, body of the .filter

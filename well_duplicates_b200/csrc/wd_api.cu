@@ -86,6 +86,12 @@ int wd_create(int device, wd_ctx **out) {
         WD_FAIL(WD_E_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e));
     }
     ctx->stream = ctx->own_stream;
+    e = cudaStreamCreateWithFlags(&ctx->copy_stream, cudaStreamNonBlocking);
+    if (e != cudaSuccess) {
+        cudaStreamDestroy(ctx->own_stream);
+        delete ctx;
+        WD_FAIL(WD_E_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e));
+    }
     // scattered 1-byte gathers: do not let L2 pull whole 64/128-byte lines from HBM (a hint; failure is harmless)
     const char *g = getenv("WELLDUP_L2_FETCH");
     cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, g ? (size_t)atoi(g) : 32);
@@ -114,12 +120,14 @@ int wd_destroy(wd_ctx *ctx) {
                       &ctx->q_flag, &ctx->descs, &ctx->order_dev, &ctx->packed, &ctx->per_target, &ctx->counters,
                       &ctx->publish, &ctx->dup_rows, &ctx->dup_count, &ctx->gs_idx, &ctx->gs_packed, &ctx->gs_codes,
                       &ctx->targets.tgt_off, &ctx->targets.slot_well, &ctx->targets.slot_level, &ctx->targets.slot_csr,
-                      &ctx->targets.level_len, &ctx->x_packed, &ctx->x_counts};
+                      &ctx->targets.level_len, &ctx->targets.visit, &ctx->x_packed, &ctx->x_counts};
     for (DevBuf *b : bufs) b->release();
     for (TileSlot &s : ctx->slots) {
         s.planes.release(); s.filter.release(); s.pfmask.release(); s.pfrank.release();
-        s.kind_dev.release(); s.pfcount_dev.release();
+        s.kind_dev.release(); s.pfcount_dev.release(); s.head.release();
     }
+    for (cudaEvent_t ev : ctx->copy_events) cudaEventDestroy(ev);
+    if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
     return WD_OK;
@@ -148,6 +156,12 @@ int wd_host_alloc(size_t bytes, void **out) {
 
 int wd_host_free(void *p) {
     if (p) WD_CUDA(cudaFreeHost(p));
+    return WD_OK;
+}
+
+int wd_last_count_h2d_bytes(wd_ctx *ctx, uint64_t *out) {
+    if (ctx == nullptr || out == nullptr) WD_FAIL(WD_E_ARG, "wd_last_count_h2d_bytes: null argument");
+    *out = ctx->last_h2d_bytes;
     return WD_OK;
 }
 
@@ -237,6 +251,9 @@ int wd_targets_load(wd_ctx *ctx, const uint32_t *centres, const uint32_t *level_
         }
     }
     tgt_off[t] = pos;
+    std::vector<uint32_t> visit(t);
+    for (uint32_t i = 0; i < t; ++i) visit[i] = i;
+    std::stable_sort(visit.begin(), visit.end(), [&](uint32_t x, uint32_t y) { return centres[x] < centres[y]; });
     TargetList &tl = ctx->targets;
     cudaStream_t st = ctx->stream;
     WD_CUDA(cudaStreamSynchronize(st));
@@ -245,6 +262,8 @@ int wd_targets_load(wd_ctx *ctx, const uint32_t *centres, const uint32_t *level_
     WD_TRY(tl.slot_csr.reserve((size_t)n_slots * 4));
     WD_TRY(tl.slot_level.reserve((size_t)n_slots));
     WD_TRY(tl.level_len.reserve(nseg * 4));
+    WD_TRY(tl.visit.reserve((size_t)t * 4));
+    WD_CUDA(cudaMemcpyAsync(tl.visit.p, visit.data(), (size_t)t * 4, cudaMemcpyHostToDevice, st));
     WD_CUDA(cudaMemcpyAsync(tl.tgt_off.p, tgt_off.data(), (size_t)(t + 1) * 4, cudaMemcpyHostToDevice, st));
     WD_CUDA(cudaMemcpyAsync(tl.slot_well.p, slot_well.data(), (size_t)n_slots * 4, cudaMemcpyHostToDevice, st));
     WD_CUDA(cudaMemcpyAsync(tl.slot_csr.p, slot_csr.data(), (size_t)n_slots * 4, cudaMemcpyHostToDevice, st));
@@ -283,6 +302,7 @@ int wd_tile_begin(wd_ctx *ctx, int tile_slot, uint32_t n_clusters, int n_planes)
     s.kind_dirty = true;
     s.has_excl = false;
     s.mapped = nullptr;
+    s.mapped_host = nullptr;
     s.mapped_filter = nullptr;
     s.mapped_filter_host = nullptr;
     return WD_OK;
@@ -344,6 +364,7 @@ int wd_tile_map_host(wd_ctx *ctx, int tile_slot, uint32_t n_clusters, int n_plan
     s.rank_valid = false;
     s.kind_dirty = true;
     s.mapped = static_cast<const uint8_t *>(attr.devicePointer);
+    s.mapped_host = planes;
     s.mapped_filter = filter ? static_cast<const uint8_t *>(fattr.devicePointer) : nullptr;
     s.mapped_filter_host = filter;
     return WD_OK;

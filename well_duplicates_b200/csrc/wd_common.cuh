@@ -61,14 +61,20 @@ struct TileDesc {                 // what the kernels see (array in device memor
     const uint8_t *kind;          // n_planes bytes: WD_PLANE_*
     uint32_t n;                   // wells on the tile
     uint32_t flags;               // bit0: pfmask / pfrank are valid
+    // host-mapped tiles only: the planes of the first compared positions are copied to HBM by DMA
+    // (head[j] = plane of position j); head_delta = head - planes (mod 2^64), so planes + head_delta
+    // + j * head_stride addresses them
+    unsigned long long head_delta;
+    unsigned long long head_stride;
 };
 
 struct TileSlot {
     uint32_t n = 0;
     int n_planes = 0;
     size_t stride = 0;
-    DevBuf planes, filter, pfmask, pfrank, kind_dev, pfcount_dev;
+    DevBuf planes, filter, pfmask, pfrank, kind_dev, pfcount_dev, head;
     const uint8_t *mapped = nullptr;   // planes left in pinned host memory (wd_tile_map_host): device view of it
+    const uint8_t *mapped_host = nullptr;     // ... and the host view (source of DMA copies)
     const uint8_t *mapped_filter = nullptr;   // same for the filter bytes (optional)
     const uint8_t *mapped_filter_host = nullptr;
     std::vector<uint8_t> kind;
@@ -94,6 +100,9 @@ struct TargetList {
     DevBuf slot_level;   // u8  [n_slots]
     DevBuf slot_csr;     // u32 [n_slots]  (centre: UINT32_MAX)
     DevBuf level_len;    // u32 [t*levels] wells per ring (LENGTH of the reference)
+    DevBuf visit;        // u32 [t] targets in ascending order of their centre well: the fused kernel walks
+                         //         them in this order, so that a CTA's targets sit on neighbouring rows of a
+                         //         plane (few pages / DRAM rows per CTA); results are stored by target ordinal
     std::vector<uint32_t> h_idx;   // host copy of the caller's idx[] (duplicate-pair log)
 };
 
@@ -103,6 +112,8 @@ struct wd_ctx {
     int device = 0;
     cudaStream_t own_stream = nullptr;
     cudaStream_t stream = nullptr;
+    cudaStream_t copy_stream = nullptr;          // DMA of head planes, overlapped with the counting kernels
+    std::vector<cudaEvent_t> copy_events;
     int sm_count = 148;
     uint64_t launches = 0;
 
@@ -127,6 +138,7 @@ struct wd_ctx {
     bool last_per_target = false;
     size_t publish_n = 0;
     size_t dup_cap = 0;
+    uint64_t last_h2d_bytes = 0;      // bytes the last wd_count copied to HBM itself (head planes of host-mapped tiles)
 };
 
 namespace wd {

@@ -103,6 +103,8 @@ static TileDesc make_desc(const TileSlot &s) {
     d.kind = s.kind_dev.as<uint8_t>();
     d.n = s.n;
     d.flags = s.rank_valid ? 1u : 0u;
+    d.head_stride = ((unsigned long long)s.n + 255ull) & ~255ull;
+    d.head_delta = (unsigned long long)(uintptr_t)s.head.as<uint8_t>() - (unsigned long long)(uintptr_t)d.planes;
     return d;
 }
 
@@ -259,7 +261,7 @@ unpack_codes_kernel(const uint64_t *__restrict__ packed, uint32_t n_idx, int len
 // ============================================================================
 struct CountArgs {
     const TileDesc *descs;
-    const uint32_t *tgt_off, *slot_well, *slot_csr, *level_len;
+    const uint32_t *tgt_off, *slot_well, *slot_csr, *level_len, *visit;
     const uint8_t *slot_level;
     const unsigned long long *g_off;
     const uint8_t *g_kind;
@@ -273,6 +275,7 @@ struct CountArgs {
     int levels, len, e, hamming;
     int step0, step1;                // fused kernel: cycles read per round (first, later), 1..16
     int cchunk;                      // fused kernel: centre cycles decoded per warp-wide load (8, 16 or 32)
+    int n_head;                      // fused kernel: positions 0..n_head-1 are read from the tile's head planes in HBM
 };
 
 // Per-warp tallies -> per_target row and the CTA's shared counters.
@@ -461,6 +464,11 @@ fused_count_kernel(CountArgs a) {
     const uint32_t tile = blockIdx.y;
     const TileDesc d = a.descs[tile];
     const int len = a.len, e = a.e;
+    if (a.n_head) {
+        // this CTA serves one tile: point its first positions at the tile's head planes
+        for (int i = threadIdx.x; i < a.n_head; i += blockDim.x) s_off[i] = d.head_delta + (unsigned long long)i * d.head_stride;
+        __syncthreads();
+    }
     // Levenshtein <= 1 <=> Hamming <= 1 on equal lengths (an indel pair costs 2)
     const bool ham_like = a.hamming != 0 || e < 2;
     const int k = ham_like ? 0 : (e >> 1);
@@ -475,6 +483,7 @@ fused_count_kernel(CountArgs a) {
         if (lane == 0) t = t_begin + atomicAdd(&s_next, 1u);
         t = __shfl_sync(0xffffffffu, t, 0);
         if (t >= t_end) break;
+        if (a.visit) t = __ldg(a.visit + t);              // spatial visiting order; results go by target ordinal
         const uint32_t s0 = __ldg(a.tgt_off + t), s1 = __ldg(a.tgt_off + t + 1);
         const uint32_t centre = __ldg(a.slot_well + s0);
         const bool valid = (__ldg(d.filter + centre) & 1u) != 0;
@@ -760,6 +769,7 @@ int count_async(wd_ctx *ctx, int first_slot, int n_tiles, const int32_t *order, 
     a.slot_well = tl.slot_well.as<uint32_t>();
     a.slot_csr = tl.slot_csr.as<uint32_t>();
     a.level_len = tl.level_len.as<uint32_t>();
+    a.visit = getenv("WELLDUP_NO_VISIT_ORDER") ? nullptr : tl.visit.as<uint32_t>();
     a.slot_level = tl.slot_level.as<uint8_t>();
     a.g_off = ctx->order_dev.as<unsigned long long>();
     a.g_kind = ctx->order_dev.as<uint8_t>() + (size_t)MAX_ORDER * 8;
@@ -814,12 +824,75 @@ int count_async(wd_ctx *ctx, int first_slot, int n_tiles, const int32_t *order, 
     } else {
         ctx->dup_cap = 0;
     }
-    switch (words) {
-        case 1: launch_count_w<1>(ctx, a, n_tiles, mode, all_bcl); break;
-        case 2: launch_count_w<2>(ctx, a, n_tiles, mode, all_bcl); break;
-        case 4: launch_count_w<4>(ctx, a, n_tiles, mode, all_bcl); break;
-        case 8: launch_count_w<8>(ctx, a, n_tiles, mode, all_bcl); break;
-        default: launch_count_w<16>(ctx, a, n_tiles, mode, all_bcl); break;
+    a.n_head = 0;
+    ctx->last_h2d_bytes = 0;
+    if (mode == 0 && over_pcie) {
+        // Host-mapped tiles: the planes every ring well is read from -- the first positions -- go to HBM
+        // by DMA (bandwidth-bound, ~52 GB/s) while the kernel pulls only what the survivors need of the
+        // later planes as 32-byte sector reads (request-bound, ~0.3 G requests/s): the two limits of the
+        // PCIe path are used side by side, group of tiles after group of tiles.
+        int n_head = 2, n_groups = 16;              // profiles/r01_notes.md: sweep on the B200 box
+        if (const char *hp = getenv("WELLDUP_HEAD_PLANES")) n_head = atoi(hp);
+        if (const char *hg = getenv("WELLDUP_HEAD_GROUPS")) n_groups = atoi(hg);
+        n_head = std::max(0, std::min(n_head, std::min(seq_len, 16)));
+        for (int k = 0; k < n_tiles; ++k)
+            if (ctx->slots[first_slot + k].mapped == nullptr)
+                WD_FAIL(WD_E_ARG, "wd_count: host-mapped and staged tile slots cannot share one call");
+        if (n_head > 0) {
+            n_groups = std::max(1, std::min(n_groups, n_tiles));
+            a.n_head = n_head;
+            if (!getenv("WELLDUP_STEPS")) {
+                a.step0 = n_head;            // first round entirely from HBM
+                a.step1 = 1;
+            }
+            const size_t hstride = ((size_t)ctx->slots[first_slot].n + 255) & ~(size_t)255;
+            for (int k = 0; k < n_tiles; ++k) WD_TRY(ctx->slots[first_slot + k].head.reserve(hstride * n_head));
+            WD_TRY(upload_descs(ctx, first_slot, n_tiles));       // head pointers may have moved
+            while ((int)ctx->copy_events.size() < n_groups + 1) {
+                cudaEvent_t ev;
+                WD_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+                ctx->copy_events.push_back(ev);
+            }
+            // the copies may not overtake earlier work on the compute stream that still reads the head buffers
+            WD_CUDA(cudaEventRecord(ctx->copy_events[n_groups], st));
+            WD_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_events[n_groups], 0));
+            const size_t row = 1 + 2 * (size_t)L;
+            for (int g = 0; g < n_groups; ++g) {
+                const int t0 = (int)((long long)n_tiles * g / n_groups), t1 = (int)((long long)n_tiles * (g + 1) / n_groups);
+                for (int k = t0; k < t1; ++k) {
+                    TileSlot &s = ctx->slots[first_slot + k];
+                    for (int j = 0; j < n_head; ++j) {
+                        const int pl = order[j];
+                        const size_t bytes = s.kind[pl] == WD_PLANE_BCL ? (size_t)s.n_block[pl] : ((size_t)s.n_block[pl] + 1) / 2;
+                        WD_CUDA(cudaMemcpyAsync(s.head.as<uint8_t>() + (size_t)j * hstride, s.mapped_host + (size_t)pl * s.stride,
+                                                bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
+                        ctx->last_h2d_bytes += bytes;
+                    }
+                }
+                WD_CUDA(cudaEventRecord(ctx->copy_events[g], ctx->copy_stream));
+                WD_CUDA(cudaStreamWaitEvent(st, ctx->copy_events[g], 0));
+                CountArgs ag = a;
+                ag.descs = a.descs + t0;
+                ag.counters = a.counters + (size_t)t0 * width;
+                if (a.per_target) ag.per_target = a.per_target + (size_t)t0 * tl.t * row;
+                switch (words) {
+                    case 1: launch_count_w<1>(ctx, ag, t1 - t0, mode, all_bcl); break;
+                    case 2: launch_count_w<2>(ctx, ag, t1 - t0, mode, all_bcl); break;
+                    case 4: launch_count_w<4>(ctx, ag, t1 - t0, mode, all_bcl); break;
+                    case 8: launch_count_w<8>(ctx, ag, t1 - t0, mode, all_bcl); break;
+                    default: launch_count_w<16>(ctx, ag, t1 - t0, mode, all_bcl); break;
+                }
+            }
+        }
+    }
+    if (a.n_head == 0) {
+        switch (words) {
+            case 1: launch_count_w<1>(ctx, a, n_tiles, mode, all_bcl); break;
+            case 2: launch_count_w<2>(ctx, a, n_tiles, mode, all_bcl); break;
+            case 4: launch_count_w<4>(ctx, a, n_tiles, mode, all_bcl); break;
+            case 8: launch_count_w<8>(ctx, a, n_tiles, mode, all_bcl); break;
+            default: launch_count_w<16>(ctx, a, n_tiles, mode, all_bcl); break;
+        }
     }
     WD_CUDA(cudaGetLastError());
     ctx->last_tiles = n_tiles;

@@ -72,6 +72,11 @@ class Engine:
         _lib.check(self._lib.wd_launch_count(self._h, C.byref(n)))
         return n.value
 
+    def last_count_h2d_bytes(self):
+        n = C.c_uint64()
+        _lib.check(self._lib.wd_last_count_h2d_bytes(self._h, C.byref(n)))
+        return n.value
+
     # ---- stage 1 --------------------------------------------------------------
     def load_locs(self, xy):
         xy = _c(xy, np.float32).reshape(-1, 2)
