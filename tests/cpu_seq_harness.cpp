@@ -97,7 +97,11 @@ static int head32(const uint8_t *a, const uint8_t *b, int len, int e, int ham) {
         wd::pseq_set<W>(pa, i, a[i]);
         wd::pseq_set<W>(pb, i, b[i]);
     }
-    return wd::head32_rejects<W>(pa, pb, len, e, ham != 0 || e < 2) ? 1 : 0;
+    if (e < 0) return 1;
+    if (e >= len) return 0;                      // the kernel does not compare sequences then
+    wd::Head32Sets s;
+    s.set(pa.lo[0], pa.hi[0], wd::head32_k(e, ham != 0));
+    return wd::popc32(s.unmatched((uint32_t)pb.lo[0], (uint32_t)pb.hi[0])) > e ? 1 : 0;
 }
 
 // 1 when the 32-symbol pre-filter of exhaustive mode rejects the pair

@@ -7,8 +7,9 @@ import sys
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libwelldup.so")
-SOURCES = ["wd_api.cu", "wd_stage1.cu", "wd_stage23.cu"]
-HEADERS = ["wd_common.cuh", "wd_scan.cuh", "wd_seq.cuh", os.path.join("..", "..", "include", "welldup.h")]
+SOURCES = ["wd_inst23_w16.cu", "wd_inst23_w8.cu", "wd_inst23_w4.cu", "wd_inst23_w2.cu", "wd_inst23_w1.cu",
+           "wd_api.cu", "wd_stage1.cu", "wd_stage23.cu", "wd_exhaustive.cu"]
+HEADERS = ["wd_common.cuh", "wd_scan.cuh", "wd_seq.cuh", "wd_pack.cuh", "wd_kernels23.cuh", os.path.join("..", "..", "include", "welldup.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]
 
@@ -38,7 +39,9 @@ def build(force=False, verbose=False):
             sys.stderr.write(out)
         if p.returncode:
             raise RuntimeError("nvcc failed on %s" % src)
-    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a"]
+    # --no-undefined: a kernel flavour that no translation unit instantiates must fail here, not at dlopen
+    cmd = [nvcc, "-shared", "-o", LIB] + objs + ["-gencode", "arch=compute_100a,code=sm_100a",
+                                                 "-Xlinker", "--no-undefined"]
     subprocess.check_call(cmd)
     return LIB
 

@@ -131,7 +131,11 @@ struct wd_ctx {
     wd::TargetList targets;
     wd::DevBuf descs, order_dev, packed, per_target, counters, publish, dup_rows, dup_count;
     wd::DevBuf gs_idx, gs_packed, gs_codes;
-    wd::DevBuf x_packed, x_counts;   // exhaustive mode
+    // exhaustive mode (wd_exhaustive.cu)
+    wd::DevBuf x_packed, x_counts, x_pre, x_ringlen, x_flags;
+    int x_geom_levels = 0;            // ring sizes in x_ringlen are valid for (levels, window); 0 = none
+    uint32_t x_geom_wlo = 0, x_geom_whi = 0, x_geom_first_empty = 0;
+    bool x_geom_overflow = false;
     // last count
     int last_tiles = 0, last_levels = 0, last_first_slot = 0;
     uint32_t last_t = 0;
@@ -161,4 +165,5 @@ int publish_counters(wd_ctx *ctx, const int32_t *tile_row, const int32_t *lane_r
 int count_exhaustive(wd_ctx *ctx, int slot, const int32_t *order, int seq_len, int levels,
                      uint32_t wlo, uint32_t whi, int e, int hamming, int64_t *tile_counters);
 int upload_descs(wd_ctx *ctx, int first_slot, int n_tiles);
+int pack_dense(wd_ctx *ctx, int slot, const int32_t *order, int seq_len, int *words_out);
 }  // namespace wd

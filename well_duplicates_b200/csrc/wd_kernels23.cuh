@@ -1,0 +1,480 @@
+// Stage 2/3 kernel templates (K4/K5 gather-decode, K6 compare + count, the fused
+// production kernel) and their launchers.  The templates are instantiated once per
+// word count W in wd_inst23_w*.cu, so that the five flavours compile in parallel;
+// wd_stage23.cu holds the host side and only sees `extern template` declarations.
+#pragma once
+#include "wd_common.cuh"
+#include "wd_pack.cuh"
+#include "wd_seq.cuh"
+
+namespace wd {
+
+constexpr int MAX_ORDER = WD_MAX_SEQ_LEN;
+
+__device__ __forceinline__ int pf_rank(const TileDesc &d, uint32_t well) {
+    const uint64_t m = __ldg(d.pfmask + (well >> 6));
+    const int b = well & 63;
+    if (!((m >> b) & 1ull)) return -1;
+    return (int)(__ldg(d.pfrank + (well >> 6)) + (uint32_t)__popcll(m & ((1ull << b) - 1ull)));
+}
+
+// ============================================================================
+// K4 / K5: gather-decode one well into packed words
+// ============================================================================
+// s_off[p]  = byte offset of the plane that supplies sequence position p
+// s_kind[p] = WD_PLANE_* of that plane (same for every tile of a launch)
+// one base call -> raw code: 0 = no-call, otherwise base = code & 3
+template <bool ALL_BCL>
+__device__ __forceinline__ uint32_t load_call(const TileDesc &d, uint32_t well, int rank, unsigned long long off,
+                                              int kind) {
+    if (ALL_BCL || kind == WD_PLANE_BCL) return __ldg(d.planes + off + well);
+    const int wi = kind == WD_PLANE_CBCL_EXCL ? rank : (int)well;
+    if (wi < 0) return 0u;                        // not PF: the block has no entry for it -> N
+    const uint32_t byte = __ldg(d.planes + off + ((uint32_t)wi >> 1));
+    return (wi & 1) ? (byte >> 4) : (byte & 15u);
+}
+
+// N (8 or 16) consecutive sequence positions p .. p+N-1 (those >= len
+// contribute nothing) -> N-bit groups of the three planes.  All N loads are
+// issued before any is consumed (memory-level parallelism).
+template <bool ALL_BCL, int N>
+__device__ __forceinline__ void decode_n(const TileDesc &d, uint32_t well, int rank, const unsigned long long *s_off,
+                                         const uint8_t *s_kind, int p, int len, uint32_t &glo, uint32_t &ghi,
+                                         uint32_t &gnn) {
+    uint32_t code[N];
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        code[j] = 4u;                            // beyond the sequence: no bit in any plane
+        if (p + j < len) code[j] = load_call<ALL_BCL>(d, well, rank, s_off[p + j], ALL_BCL ? 0 : s_kind[p + j]);
+    }
+    glo = ghi = gnn = 0;
+#pragma unroll
+    for (int j = 0; j < N; ++j) {
+        const uint32_t b = code[j];
+        glo |= (b & 1u) << j;
+        ghi |= ((b >> 1) & 1u) << j;
+        gnn |= (b == 0u ? 1u : 0u) << j;
+    }
+}
+
+template <int W>
+__device__ __forceinline__ void pseq_or_group(PSeq<W> &q, int p, uint32_t glo, uint32_t ghi, uint32_t gnn) {
+    const int w = p >> 6, sh = p & 63;           // groups start at multiples of their size: none straddles a word
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        if (i == w) {
+            q.lo[i] |= (uint64_t)glo << sh;
+            q.hi[i] |= (uint64_t)ghi << sh;
+            q.nn[i] |= (uint64_t)gnn << sh;
+        }
+    }
+}
+
+template <int W, bool ALL_BCL>
+__device__ __forceinline__ void decode_well(const TileDesc &d, uint32_t well, const unsigned long long *s_off,
+                                            const uint8_t *s_kind, int len, PSeq<W> &out) {
+    int rank = 0;
+    if (!ALL_BCL && (d.flags & 1u)) rank = pf_rank(d, well);
+    pseq_clear(out);
+    for (int p = 0; p < len; p += 8) {
+        uint32_t glo, ghi, gnn;
+        decode_n<ALL_BCL, 8>(d, well, rank, s_off, s_kind, p, len, glo, ghi, gnn);
+        pseq_or_group<W>(out, p, glo, ghi, gnn);
+    }
+}
+
+__device__ __forceinline__ void load_order(const unsigned long long *g_off, const uint8_t *g_kind, int len,
+                                           unsigned long long *s_off, uint8_t *s_kind) {
+    for (int i = threadIdx.x; i < len; i += blockDim.x) {
+        s_off[i] = g_off[i];
+        s_kind[i] = g_kind[i];
+    }
+    __syncthreads();
+}
+
+// one thread per (tile, slot): packed[tile][slot][W][4]
+template <int W, bool ALL_BCL>
+__global__ void __launch_bounds__(256)
+gather_pack_kernel(const TileDesc *__restrict__ descs, const uint32_t *__restrict__ slot_well, uint32_t n_slots,
+                   const unsigned long long *__restrict__ g_off, const uint8_t *__restrict__ g_kind, int len,
+                   uint64_t *__restrict__ packed) {
+    __shared__ unsigned long long s_off[MAX_ORDER];
+    __shared__ uint8_t s_kind[MAX_ORDER];
+    load_order(g_off, g_kind, len, s_off, s_kind);
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_slots) return;
+    const TileDesc d = descs[blockIdx.y];
+    const uint32_t well = slot_well ? __ldg(slot_well + s) : s;     // null: every well in index order (exhaustive mode)
+    PSeq<W> q;
+    decode_well<W, ALL_BCL>(d, well, s_off, s_kind, len, q);
+    const uint64_t meta = __ldg(d.filter + well) & 1u;
+    store_packed<W>(packed + ((size_t)blockIdx.y * n_slots + s) * (size_t)(W * PACK_STRIDE), q, meta);
+}
+
+// packed -> one byte per symbol (0..3 ACGT, 4 N) for wd_get_seqs
+template <int W>
+__global__ void __launch_bounds__(256)
+unpack_codes_kernel(const uint64_t *__restrict__ packed, uint32_t n_idx, int len, uint8_t *__restrict__ codes,
+                    uint8_t *__restrict__ pf) {
+    const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= n_idx) return;
+    PSeq<W> q;
+    const uint64_t meta = load_packed<W>(packed + (size_t)s * (W * PACK_STRIDE), q);
+    pf[s] = (uint8_t)(meta & 1u);
+    for (int p = 0; p < len; ++p) {
+        const unsigned c = pseq_get<W>(q, p);
+        codes[(size_t)s * len + p] = (uint8_t)((c & 4u) ? 4u : c);
+    }
+}
+
+// ============================================================================
+// K6: compare + count
+// ============================================================================
+struct CountArgs {
+    const TileDesc *descs;
+    const uint32_t *tgt_off, *slot_well, *slot_csr, *level_len, *visit;
+    const uint8_t *slot_level;
+    const unsigned long long *g_off;
+    const uint8_t *g_kind;
+    const uint64_t *packed;          // two-pass only
+    int32_t *per_target;             // may be null
+    unsigned long long *counters;    // [tiles][1+5L]
+    int32_t *dup_rows;               // may be null: (tile, target, csr position, distance)
+    unsigned long long *dup_count;
+    unsigned long long dup_cap;
+    uint32_t t, n_slots;
+    int levels, len, e, hamming;
+    int step0, step1;                // fused kernel: cycles read per round (first, later), 1..16
+    int cchunk;                      // fused kernel: centre cycles decoded per warp-wide load (8, 16 or 32)
+    int n_head;                      // fused kernel: positions 0..n_head-1 are read from the tile's head planes in HBM
+};
+
+// Per-warp tallies -> per_target row and the CTA's shared counters.
+template <int LMAX>
+__device__ __forceinline__ void finish_target(const CountArgs &a, uint32_t tile, uint32_t t, int lane, bool valid,
+                                              const uint32_t *dups, uint32_t *s_cnt) {
+    const int L = a.levels;
+    const int row = 1 + 2 * L;
+    if (a.per_target != nullptr) {
+        int32_t *pt = a.per_target + ((size_t)tile * a.t + t) * row;
+        if (lane == 0) pt[0] = valid ? 1 : 0;
+#pragma unroll
+        for (int l = 0; l < LMAX; ++l) {
+            if (l < L && lane == l) {
+                pt[1 + 2 * l] = valid ? (int32_t)dups[l] : 0;
+                pt[2 + 2 * l] = valid ? (int32_t)__ldg(a.level_len + (size_t)t * L + l) : 0;
+            }
+        }
+    }
+    if (!valid) return;
+    // AccO: a hit at this level or further in; AccI: at this level or further out
+    // (count_well_duplicates.py:77-89)
+    uint32_t hit_mask = 0;
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l)
+        if (l < L && dups[l]) hit_mask |= 1u << l;
+    if (lane == 0) atomicAdd(&s_cnt[0], 1u);
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l) {
+        if (l < L && lane == l) {
+            uint32_t *c = s_cnt + 1 + 5 * l;
+            atomicAdd(c + 0, __ldg(a.level_len + (size_t)t * L + l));
+            if (dups[l]) {
+                atomicAdd(c + 1, dups[l]);
+                atomicAdd(c + 2, 1u);
+            }
+            if (hit_mask & ((2u << l) - 1u)) atomicAdd(c + 3, 1u);
+            if (hit_mask >> l) atomicAdd(c + 4, 1u);
+        }
+    }
+}
+
+template <int W>
+__device__ __forceinline__ void log_dup(const CountArgs &a, uint32_t tile, uint32_t t, uint32_t slot,
+                                        const PSeq<W> &c, const PSeq<W> &b) {
+    const unsigned long long pos = atomicAdd(a.dup_count, 1ull);
+    if (pos < a.dup_cap) {
+        int32_t *r = a.dup_rows + pos * 4;
+        r[0] = (int32_t)tile;
+        r[1] = (int32_t)t;
+        r[2] = (int32_t)__ldg(a.slot_csr + slot);
+        r[3] = exact_distance<W>(c, b, a.len, a.hamming != 0);
+    }
+}
+
+__device__ __forceinline__ void flush_counters(uint32_t *s_cnt, unsigned long long *dst, int n) {
+    __syncthreads();
+    for (int i = threadIdx.x; i < n; i += blockDim.x)
+        if (s_cnt[i]) atomicAdd(dst + i, (unsigned long long)s_cnt[i]);
+}
+
+constexpr int CNT_WARPS = 8;
+
+// two-pass flavour: reads the packed words K4/K5 left in HBM.  One warp per
+// (tile, target); lanes stride over the target's ring slots.
+template <int W, int LMAX>
+__global__ void __launch_bounds__(CNT_WARPS * 32)
+compare_count_kernel(CountArgs a) {
+    __shared__ uint32_t s_cnt[1 + 5 * LMAX];
+    for (int i = threadIdx.x; i < 1 + 5 * LMAX; i += blockDim.x) s_cnt[i] = 0;
+    __syncthreads();
+    const int lane = threadIdx.x & 31;
+    const uint32_t tile = blockIdx.y;
+    const uint32_t t = blockIdx.x * CNT_WARPS + (threadIdx.x >> 5);
+    if (t < a.t) {
+        const uint32_t s0 = __ldg(a.tgt_off + t), s1 = __ldg(a.tgt_off + t + 1);
+        const uint64_t *tp = a.packed + (size_t)tile * a.n_slots * (W * PACK_STRIDE);
+        PSeq<W> c;
+        const uint64_t meta = load_packed<W>(tp + (size_t)s0 * (W * PACK_STRIDE), c);
+        const bool valid = (meta & 1ull) != 0;
+        uint32_t dups[LMAX];
+#pragma unroll
+        for (int l = 0; l < LMAX; ++l) dups[l] = 0;
+        if (valid) {
+            for (uint32_t base = s0 + 1; base < s1; base += 32) {
+                const uint32_t s = base + lane;
+                bool dup = false;
+                int lvl = 0;
+                if (s < s1) {
+                    PSeq<W> b;
+                    load_packed<W>(tp + (size_t)s * (W * PACK_STRIDE), b);
+                    lvl = __ldg(a.slot_level + s);
+                    dup = is_duplicate<W>(c, b, a.len, a.e, a.hamming != 0);
+                    if (dup && a.dup_rows != nullptr) log_dup<W>(a, tile, t, s, c, b);
+                }
+#pragma unroll
+                for (int l = 0; l < LMAX; ++l)
+                    if (l < a.levels) dups[l] += __popc(__ballot_sync(0xffffffffu, dup && lvl == l + 1));
+            }
+        }
+        finish_target<LMAX>(a, tile, t, lane, valid, dups, s_cnt);
+    }
+    flush_counters(s_cnt, a.counters + (size_t)tile * (1 + 5 * a.levels), 1 + 5 * a.levels);
+}
+
+// fused flavour (production): the warp gathers and decodes its target's wells
+// straight from the planes, compares in registers and never writes the packed
+// words.  What it reads is decided symbol by symbol:
+//  * targets whose centre fails the filter are skipped before any plane byte
+//    is read;
+//  * ring wells are read a few cycles at a time, one well per lane, and fed to
+//    the incremental edit-distance programme of wd_seq.cuh (PrefixDP; a running
+//    mismatch count for --hamming / e < 2).  A well stops being read as soon as
+//    its prefix proves dist > e -- 96 % of unrelated reads after 6 symbols --
+//    so the later planes are touched only around real duplicates;
+//  * the centre is decoded by the whole warp (lane = cycle, three ballots turn
+//    the calls into bit-plane words), 8-32 cycles at a time and only as
+//    far ahead as the programme needs (k = e/2 symbols past the ring wells): a
+//    target without duplicates never reads its centre beyond the first chunks.
+constexpr int FUSED_TPB = 64;    // targets per CTA; its 8 warps pull them from a shared counter
+
+// raw call (0 = no-call, else base = raw & 3) -> symbol 0..3, 4 = N
+__device__ __forceinline__ uint32_t call_symbol(uint32_t raw) { return raw == 0u ? 4u : (raw & 3u); }
+
+// n <= 16 bits of a W-word bit string starting at bit p
+template <int W>
+__device__ __forceinline__ uint32_t bits_at(const uint64_t *plane, int p, int n) {
+    const int w = p >> 6, sh = p & 63;
+    uint64_t v = 0;
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        if (i == w) v |= plane[i] >> sh;
+        if (i == w + 1 && sh != 0) v |= plane[i] << (64 - sh);
+    }
+    return (uint32_t)v & ((1u << n) - 1u);
+}
+
+// NMAX calls of one well at sequence positions p .. p+n-1, all loads in flight together
+template <bool ALL_BCL, int NMAX>
+__device__ __forceinline__ void load_calls(const TileDesc &d, uint32_t well, int rank, const unsigned long long *s_off,
+                                           const uint8_t *s_kind, int p, int n, uint32_t (&raw)[NMAX]) {
+#pragma unroll
+    for (int j = 0; j < NMAX; ++j) {
+        raw[j] = 0u;
+        if (j < n) raw[j] = load_call<ALL_BCL>(d, well, rank, s_off[p + j], ALL_BCL ? 0 : s_kind[p + j]);
+    }
+}
+
+template <int W, bool ALL_BCL, int NMAX>
+__device__ __forceinline__ bool ring_round(const TileDesc &d, uint32_t well, int rank, const unsigned long long *s_off,
+                                           const uint8_t *s_kind, const PSeq<W> &c, int known_c, int len, int p, int n,
+                                           int k, int e, bool ham_like, PrefixDP<W> &dp, int &mism) {
+    uint32_t raw[NMAX];
+    load_calls<ALL_BCL, NMAX>(d, well, rank, s_off, s_kind, p, n, raw);
+    if (ham_like) {
+        uint32_t glo = 0, ghi = 0, gnn = 0;
+#pragma unroll
+        for (int j = 0; j < NMAX; ++j) {
+            if (j < n) {
+                const uint32_t sym = call_symbol(raw[j]);
+                glo |= (sym & 1u) << j;
+                ghi |= ((sym >> 1) & 1u) << j;
+                gnn |= (sym >> 2) << j;
+            }
+        }
+        mism += __popc((bits_at<W>(c.lo, p, n) ^ glo) | (bits_at<W>(c.hi, p, n) ^ ghi) | (bits_at<W>(c.nn, p, n) ^ gnn));
+        return mism <= e;
+    }
+#pragma unroll
+    for (int j = 0; j < NMAX; ++j)
+        if (j < n) pdp_step<W>(dp, c, known_c, len, p + j, k, call_symbol(raw[j]));
+    return pdp_band_min<W>(dp, len, p + n, k) <= e;
+}
+
+template <int W, int LMAX, bool ALL_BCL>
+__global__ void __launch_bounds__(CNT_WARPS * 32)
+fused_count_kernel(CountArgs a) {
+    __shared__ unsigned long long s_off[MAX_ORDER];
+    __shared__ uint8_t s_kind[MAX_ORDER];
+    __shared__ uint32_t s_cnt[1 + 5 * LMAX];
+    __shared__ uint32_t s_next;
+    for (int i = threadIdx.x; i < 1 + 5 * LMAX; i += blockDim.x) s_cnt[i] = 0;
+    if (threadIdx.x == 0) s_next = 0;
+    load_order(a.g_off, a.g_kind, a.len, s_off, s_kind);
+    const int lane = threadIdx.x & 31;
+    const uint32_t tile = blockIdx.y;
+    const TileDesc d = a.descs[tile];
+    const int len = a.len, e = a.e;
+    if (a.n_head) {
+        // this CTA serves one tile: point its first positions at the tile's head planes
+        for (int i = threadIdx.x; i < a.n_head; i += blockDim.x) s_off[i] = d.head_delta + (unsigned long long)i * d.head_stride;
+        __syncthreads();
+    }
+    // Levenshtein <= 1 <=> Hamming <= 1 on equal lengths (an indel pair costs 2)
+    const bool ham_like = a.hamming != 0 || e < 2;
+    const int k = ham_like ? 0 : (e >> 1);
+    const bool read_nothing = e < 0 || e >= len;       // no pair / every pair is a duplicate
+    const uint32_t t_begin = blockIdx.x * FUSED_TPB;
+    const uint32_t t_end = min(t_begin + FUSED_TPB, a.t);
+    // Targets differ a lot in cost (a failed centre costs one byte, a real
+    // duplicate keeps its warp reading to the last cycle), so warps take the
+    // next target when they are done instead of owning a fixed one.
+    for (;;) {
+        uint32_t t = 0;
+        if (lane == 0) t = t_begin + atomicAdd(&s_next, 1u);
+        t = __shfl_sync(0xffffffffu, t, 0);
+        if (t >= t_end) break;
+        if (a.visit) t = __ldg(a.visit + t);              // spatial visiting order; results go by target ordinal
+        const uint32_t s0 = __ldg(a.tgt_off + t), s1 = __ldg(a.tgt_off + t + 1);
+        const uint32_t centre = __ldg(a.slot_well + s0);
+        const bool valid = (__ldg(d.filter + centre) & 1u) != 0;
+        uint32_t dups[LMAX];
+#pragma unroll
+        for (int l = 0; l < LMAX; ++l) dups[l] = 0;
+        if (valid) {
+            PSeq<W> c;
+            pseq_clear(c);
+            int known_c = 0;
+            int crank = 0;
+            if (!ALL_BCL && (d.flags & 1u)) crank = pf_rank(d, centre);
+            for (uint32_t base = s0 + 1; base < s1; base += 32) {
+                const uint32_t s = base + lane;
+                const bool mine = s < s1;
+                uint32_t well = 0;
+                int lvl = 0, rank = 0;
+                if (mine) {
+                    well = __ldg(a.slot_well + s);
+                    lvl = __ldg(a.slot_level + s);
+                    if (!ALL_BCL && (d.flags & 1u)) rank = pf_rank(d, well);
+                }
+                PrefixDP<W> dp;
+                pdp_init(dp);
+                int mism = 0;
+                bool alive = mine && e >= 0;
+                int p = read_nothing ? len : 0;
+                while (p < len) {
+                    if (!__any_sync(0xffffffffu, alive)) break;
+                    const int n = min(p == 0 ? a.step0 : a.step1, len - p);
+                    // ---- centre: lane = cycle, as far as this round looks ahead ----------
+                    const int need = min(len, p + n + k);
+                    while (known_c < need) {
+                        const int q = known_c + lane;
+                        uint32_t sym = 0u;
+                        if (lane < a.cchunk && q < len)
+                            sym = call_symbol(load_call<ALL_BCL>(d, centre, crank, s_off[q], ALL_BCL ? 0 : s_kind[q]));
+                        const uint32_t glo = __ballot_sync(0xffffffffu, sym & 1u);
+                        const uint32_t ghi = __ballot_sync(0xffffffffu, sym & 2u);
+                        const uint32_t gnn = __ballot_sync(0xffffffffu, sym & 4u);
+                        pseq_or_group<W>(c, known_c, glo, ghi, gnn);     // chunks never straddle a word
+                        known_c = min(len, known_c + a.cchunk);
+                    }
+                    // ---- ring wells: lane = well ---------------------------------------------
+                    if (alive) {
+                        if (n > 8) alive = ring_round<W, ALL_BCL, 16>(d, well, rank, s_off, s_kind, c, known_c, len, p, n, k, e, ham_like, dp, mism);
+                        else if (n > 4) alive = ring_round<W, ALL_BCL, 8>(d, well, rank, s_off, s_kind, c, known_c, len, p, n, k, e, ham_like, dp, mism);
+                        else if (n > 2) alive = ring_round<W, ALL_BCL, 4>(d, well, rank, s_off, s_kind, c, known_c, len, p, n, k, e, ham_like, dp, mism);
+                        else alive = ring_round<W, ALL_BCL, 2>(d, well, rank, s_off, s_kind, c, known_c, len, p, n, k, e, ham_like, dp, mism);
+                    }
+                    p += n;
+                }
+                const bool dup = alive;            // survived to p == len: dist <= e
+#pragma unroll
+                for (int l = 0; l < LMAX; ++l)
+                    if (l < a.levels) dups[l] += __popc(__ballot_sync(0xffffffffu, dup && lvl == l + 1));
+            }
+        }
+        finish_target<LMAX>(a, tile, t, lane, valid, dups, s_cnt);
+    }
+    flush_counters(s_cnt, a.counters + (size_t)tile * (1 + 5 * a.levels), 1 + 5 * a.levels);
+}
+
+
+// ============================================================================
+// launchers (one explicit instantiation per W)
+// ============================================================================
+template <int W, bool ALL_BCL>
+void launch_gather(wd_ctx *ctx, const TileDesc *descs, const uint32_t *slot_well, uint32_t n_slots, int n_tiles,
+                          int len, uint64_t *packed) {
+    const unsigned long long *g_off = ctx->order_dev.as<unsigned long long>();
+    const uint8_t *g_kind = ctx->order_dev.as<uint8_t>() + (size_t)MAX_ORDER * 8;
+    dim3 grid((n_slots + 255) / 256, n_tiles);
+    gather_pack_kernel<W, ALL_BCL><<<grid, 256, 0, ctx->stream>>>(descs, slot_well, n_slots, g_off, g_kind, len, packed);
+    ctx->launches++;
+}
+
+template <int W>
+void launch_gather_w(wd_ctx *ctx, bool all_bcl, const TileDesc *descs, const uint32_t *slot_well,
+                            uint32_t n_slots, int n_tiles, int len, uint64_t *packed) {
+    if (all_bcl) launch_gather<W, true>(ctx, descs, slot_well, n_slots, n_tiles, len, packed);
+    else launch_gather<W, false>(ctx, descs, slot_well, n_slots, n_tiles, len, packed);
+}
+
+template <int W>
+void launch_unpack_w(wd_ctx *ctx, const uint64_t *packed, uint32_t n_idx, int len, uint8_t *codes, uint8_t *pf) {
+    unpack_codes_kernel<W><<<(n_idx + 255) / 256, 256, 0, ctx->stream>>>(packed, n_idx, len, codes, pf);
+    ctx->launches++;
+}
+
+template <int W, int LMAX>
+void launch_count(wd_ctx *ctx, const CountArgs &a, int n_tiles, int mode, bool all_bcl) {
+    dim3 grid((a.t + CNT_WARPS - 1) / CNT_WARPS, n_tiles);
+    dim3 fgrid((a.t + FUSED_TPB - 1) / FUSED_TPB, n_tiles);
+    if (mode == 1) {
+        compare_count_kernel<W, LMAX><<<grid, CNT_WARPS * 32, 0, ctx->stream>>>(a);
+    } else if (all_bcl) {
+        fused_count_kernel<W, LMAX, true><<<fgrid, CNT_WARPS * 32, 0, ctx->stream>>>(a);
+    } else {
+        fused_count_kernel<W, LMAX, false><<<fgrid, CNT_WARPS * 32, 0, ctx->stream>>>(a);
+    }
+    ctx->launches++;
+}
+
+template <int W>
+void launch_count_w(wd_ctx *ctx, const CountArgs &a, int n_tiles, int mode, bool all_bcl) {
+    if (a.levels <= 5) launch_count<W, 5>(ctx, a, n_tiles, mode, all_bcl);
+    else launch_count<W, WD_MAX_LEVELS>(ctx, a, n_tiles, mode, all_bcl);
+}
+
+#define WD_FOR_EACH_W(X) X(1) X(2) X(4) X(8) X(16)
+#define WD_DECLARE_W(W)                                                                                          \
+    extern template void launch_gather_w<W>(wd_ctx *, bool, const TileDesc *, const uint32_t *, uint32_t, int, int, \
+                                            uint64_t *);                                                         \
+    extern template void launch_unpack_w<W>(wd_ctx *, const uint64_t *, uint32_t, int, uint8_t *, uint8_t *);     \
+    extern template void launch_count_w<W>(wd_ctx *, const CountArgs &, int, int, bool);
+#define WD_INSTANTIATE_W(W)                                                                                      \
+    template void launch_gather_w<W>(wd_ctx *, bool, const TileDesc *, const uint32_t *, uint32_t, int, int,        \
+                                     uint64_t *);                                                                \
+    template void launch_unpack_w<W>(wd_ctx *, const uint64_t *, uint32_t, int, uint8_t *, uint8_t *);            \
+    template void launch_count_w<W>(wd_ctx *, const CountArgs &, int, int, bool);
+
+}  // namespace wd

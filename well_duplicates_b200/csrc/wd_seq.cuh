@@ -325,31 +325,41 @@ WD_HD int pdp_band_min(const PrefixDP<W> &s, int len, int p, int k) {
     return best;
 }
 
-// cheap necessary condition for dist <= e on the first 32 symbols only (32-bit
-// ops): the running mismatch count for Hamming-like tests, the shifted-Hamming
-// bound of wd_seq.cuh restricted to a 32-symbol prefix of b otherwise.  99.9 %
-// of the ring wells are unrelated reads and stop here.
-template <int W>
-WD_HD bool head32_rejects(const PSeq<W> &a, const PSeq<W> &b, int len, int e, bool ham_like) {
-    const int n = len < 32 ? len : 32;
-    const uint32_t m = n >= 32 ? ~0u : ((1u << n) - 1u);
-    const uint32_t alo = (uint32_t)a.lo[0], ahi = (uint32_t)a.hi[0], ann = (uint32_t)a.nn[0];
-    const uint32_t blo = (uint32_t)b.lo[0], bhi = (uint32_t)b.hi[0], bnn = (uint32_t)b.nn[0];
-    uint32_t all = ((alo ^ blo) | (ahi ^ bhi) | (ann ^ bnn)) & m;
-    if (!ham_like) {
-        const int k = e >> 1;
-        if (k >= 16) return false;
-        // a[j + d] for j < 32 needs bits of a up to 32 + k: take them from the 64-bit word
-        for (int d = 1; d <= k; ++d) {
-            const uint32_t ulo = (uint32_t)(a.lo[0] >> d), uhi = (uint32_t)(a.hi[0] >> d), unn = (uint32_t)(a.nn[0] >> d);
-            uint32_t up = (ulo ^ blo) | (uhi ^ bhi) | (unn ^ bnn);
-            const int cut = len - d;                                   // partner j + d must be < len
-            if (cut < 32) up |= cut <= 0 ? ~0u : ~((1u << cut) - 1u);
-            const uint32_t dn = (((alo << d) ^ blo) | ((ahi << d) ^ bhi) | ((ann << d) ^ bnn)) | ((1u << d) - 1u);
-            all &= up & dn;
+// Cheap necessary condition for dist(a, b) <= e from the first 32 symbols of b
+// (exhaustive mode, wd_exhaustive.cu), on the lo/hi planes only: N aliases to A,
+// so every true match stays a match and the count of unmatched positions can
+// only shrink (see shd_bad_count).  In an edit script of cost <= e on
+// equal-length strings every exactly matched symbol b[j] is matched to
+// a[j + d] with |d| <= k = e/2 (k = 0 for Hamming and for e < 2); all other
+// positions of b cost an edit each.  Per string a, the set
+// S_j = {a[j + d] : |d| <= k} is kept as four 32-bit planes (one per base), so
+//   unmatched(b) = ~mux(b.hi, mux(b.lo, SA, SC), mux(b.lo, SG, ST))
+// costs three logic instructions whatever k is; popc(unmatched) <= e is the
+// test.  Partners outside [0, len) read as A (zero bits): that only weakens it.
+struct Head32Sets {
+    uint32_t sa, sc, sg, st;
+    WD_HD void clear() { sa = sc = sg = st = 0u; }
+    // lo, hi: first 64-symbol word of a's base planes; k <= 31
+    WD_HD void set(uint64_t lo, uint64_t hi, int k) {
+        clear();
+        for (int d = -k; d <= k; ++d) {
+            const uint32_t l = d >= 0 ? (uint32_t)(lo >> d) : (uint32_t)lo << (-d);
+            const uint32_t h = d >= 0 ? (uint32_t)(hi >> d) : (uint32_t)hi << (-d);
+            sa |= ~l & ~h; sc |= l & ~h; sg |= ~l & h; st |= l & h;
         }
     }
-    return popc32(all & m) > e;
+    // blo, bhi: base planes of b's first 32 symbols
+    WD_HD uint32_t unmatched(uint32_t blo, uint32_t bhi) const {
+        const uint32_t t0 = (blo & sc) | (~blo & sa);
+        const uint32_t t1 = (blo & st) | (~blo & sg);
+        return ~((bhi & t1) | (~bhi & t0));
+    }
+};
+
+// k of the test above for (e, metric): Levenshtein <= 1 <=> Hamming <= 1 on equal lengths
+WD_HD int head32_k(int e, bool use_hamming) {
+    if (use_hamming || e < 2) return 0;
+    return (e >> 1) < 31 ? (e >> 1) : 31;
 }
 
 // dist(a, b) <= e under the reference's chosen metric.

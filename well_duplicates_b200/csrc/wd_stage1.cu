@@ -226,6 +226,7 @@ int locs_load(wd_ctx *ctx, const float *xy, uint32_t n) {
     WD_CUDA(cudaGetLastError());
     ctx->n_locs = n;
     ctx->q_t = 0;
+    ctx->x_geom_levels = 0;          // ring sizes of exhaustive mode belong to the previous .locs
     return WD_OK;
 }
 
