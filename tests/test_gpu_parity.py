@@ -432,6 +432,67 @@ def test_exhaustive_medium_tile_vs_oracle(eng, oracle, e, ham, levels):
     assert got[2::5].sum() > 100
 
 
+def test_exhaustive_index_window_edge(eng, oracle):
+    """Rows of 4000 wells: the wells five rows away sit at index distance
+    20000 +- 2, exactly where the reference's scan window [c - 20000, c + 20001]
+    ends (prepare_cluster_indexes.py:52-67).  The window is not symmetric, so a
+    duplicate pair may count for one of its wells and not for the other."""
+    R, CP = oracle
+    from well_duplicates_b200 import synth
+    rng = np.random.default_rng(77)
+    row_len, rows, ncyc = 4000, 12, 20
+    n = row_len * rows
+    X, Y = synth.hex_lattice(n, row_len)
+    td = synth.make_tile(rng, n, ncyc, row_len, dup_rate=0.0)
+    # plant copies five rows up and down, at every index offset around the window edge
+    planes = td.planes
+    for k, off in enumerate([19998, 19999, 20000, 20001, 20002] * 40):
+        a = int(rng.integers(0, n - 20010))
+        planes[:, a + off] = planes[:, a]
+    td.filt[:] = 1
+    eng.load_locs(synth.xy_to_locs_floats(X, Y))
+    eng.tile_begin(0, n, ncyc)
+    eng.tile_put_filter(0, td.filt)
+    for c in range(ncyc):
+        eng.tile_put_bcl(0, c, planes[c])
+    order = list(range(ncyc))
+    for ham in (False, True):
+        got = eng.count_exhaustive(0, order, 5, 2, ham)
+        want = CP.count_exhaustive(X, Y, [planes[c] for c in order], ["bcl"] * ncyc, td.filt, 5, 2, ham)
+        assert np.array_equal(got, want)
+    assert got[1 + 5 * 4 + 1] > 50            # ring-5 duplicates were found at all
+
+
+def test_exhaustive_low_complexity_reads(eng, oracle):
+    """Blocks of no-call wells (all N) beside poly-A wells: in the 32-symbol
+    pre-test an N reads as A, so these pairs all reach the exact compare, which
+    must tell them apart (N is an ordinary symbol, count_well_duplicates.py:251-252)."""
+    R, CP = oracle
+    from well_duplicates_b200 import synth
+    rng = np.random.default_rng(78)
+    n, row_len, ncyc = 24000, 200, 40
+    X, Y = synth.hex_lattice(n, row_len)
+    td = synth.make_tile(rng, n, ncyc, row_len, dup_rate=0.05, shift_share=0.5, nocall_rate=0.01)
+    for r0 in (10, 40, 41, 42, 90):
+        td.planes[:, r0 * row_len + 20:r0 * row_len + 60] = 0            # all N
+        td.planes[:, r0 * row_len + 60:r0 * row_len + 90] = 0x5c         # poly-A, quality 23
+        td.planes[:, r0 * row_len + 90:r0 * row_len + 110] = 0x5f        # poly-T
+    eng.load_locs(synth.xy_to_locs_floats(X, Y))
+    eng.tile_begin(0, n, ncyc)
+    eng.tile_put_filter(0, td.filt)
+    for c in range(ncyc):
+        eng.tile_put_bcl(0, c, td.planes[c])
+    order = list(range(ncyc))
+    for e, ham in ((2, False), (0, True), (5, False), (1, False)):
+        got = eng.count_exhaustive(0, order, 5, e, ham)
+        want = CP.count_exhaustive(X, Y, [td.planes[c] for c in order], ["bcl"] * ncyc, td.filt, 5, e, ham)
+        assert np.array_equal(got, want), (e, ham)
+    for e in (-1, 40, 100):                      # no pair / every pair is a duplicate: no sequence is compared
+        got = eng.count_exhaustive(0, order, 3, e, False)
+        want = CP.count_exhaustive(X, Y, [td.planes[c] for c in order], ["bcl"] * ncyc, td.filt, 3, e, False)
+        assert np.array_equal(got, want), e
+
+
 def test_exhaustive_errors(eng, oracle):
     R, CP = oracle
     from well_duplicates_b200 import synth

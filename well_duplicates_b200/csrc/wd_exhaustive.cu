@@ -166,167 +166,253 @@ exh_geometry_kernel(XGeomArgs a) {
 }
 
 // ============================================================================
-// per tile: 32-symbol prefixes in grid order
+// per tile: 32-symbol prefixes in grid order, tallies reset
 // ============================================================================
+constexpr unsigned long long X_INVALID = 1ull << 63;      // tally flag: the well fails the filter
+
 __global__ void __launch_bounds__(256)
 exh_prefix_kernel(const int4 *__restrict__ cell_wells, const uint64_t *__restrict__ packed, int words, uint32_t n,
-                  uint2 *__restrict__ pre) {
+                  uint2 *__restrict__ pre, unsigned long long *__restrict__ tally) {
     const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
     if (p >= n) return;
     const uint32_t well = (uint32_t)__ldg(cell_wells + p).z;
-    const ulonglong2 q = __ldg(reinterpret_cast<const ulonglong2 *>(packed + (size_t)well * words * PACK_STRIDE));
-    pre[p] = make_uint2((uint32_t)q.x, (uint32_t)q.y);          // lo, hi; an N reads as A here (necessary test only)
+    const ulonglong2 *q = reinterpret_cast<const ulonglong2 *>(packed + (size_t)well * words * PACK_STRIDE);
+    const ulonglong2 q0 = __ldg(q), q1 = __ldg(q + 1);
+    pre[p] = make_uint2((uint32_t)q0.x, (uint32_t)q0.y);        // lo, hi; an N reads as A here (necessary test only)
+    tally[p] = (q1.y & 1ull) ? 0ull : X_INVALID;                // count_well_duplicates.py:236-237
 }
 
 // ============================================================================
-// per tile: compare + count
+// per tile: compare
 // ============================================================================
+// dist() and the ring of a pair are symmetric, so every unordered pair is
+// tested ONCE, by the well that comes first in grid order: a warp's candidate
+// list is the rest of its own grid row (from its first record on, as far as
+// 102 px to the right of its last centre) and the run of the next grid row.
+// A duplicate pair is credited to both wells' tallies (ring l in bits
+// [12 l, 12 l + 12)), each under its own index window; wells that fail the
+// filter collect tallies too and are skipped by exh_finish_kernel.
 struct XCmpArgs {
     XGrid g;
     const uint2 *pre;                    // [n] grid order
-    const uint64_t *packed;              // [n][W][4] well order
-    const unsigned long long *ringlen;   // [n] grid order
-    unsigned long long *counters;        // [1 + 5 * levels]
-    int levels, len, e, hamming, k;
-    uint32_t wlo, whi;
+    const uint64_t *packed;              // [n][words][4] well order
+    uint2 *work;                         // pairs (grid record of the first well, of the second) for exh_verify_kernel
+    uint32_t *work_count;
+    uint32_t work_cap;
+    int words, e, k;
 };
 
-template <int W>
 __global__ void __launch_bounds__(XW * 32)
 exh_compare_kernel(XCmpArgs a) {
     __shared__ uint2 s_pre[XW][32];
-    __shared__ uint32_t s_cnt[1 + 5 * 5];
-    for (int i = threadIdx.x; i < 1 + 5 * 5; i += blockDim.x) s_cnt[i] = 0;
-    __syncthreads();
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-    const int L = a.levels;
-    const int d2_max = c_x_d2[L];
-    const bool ham = a.hamming != 0;
-    // e < 0: no pair is a duplicate; e >= len: every pair is one -- neither needs a sequence
-    const bool compare = a.e >= 0 && a.e < a.len;
+    const int need_all = 32 - a.e;                          // matched positions a pair needs among the first 32
     for (uint32_t p0 = (blockIdx.x * XW + warp) * 32u; p0 < a.g.n; p0 += gridDim.x * XW * 32u) {
         const uint32_t p = p0 + lane;
         const bool has = p < a.g.n;
         int4 me = make_int4(0, 0, 0, 0);
-        bool valid = false;                                 // count_well_duplicates.py:236-237
         Head32Sets c;                                       // the 32-symbol necessary test, wd_seq.cuh
         c.clear();
         if (has) {
             me = __ldg(a.g.cell_wells + p);
-            const ulonglong2 *q = reinterpret_cast<const ulonglong2 *>(a.packed + (size_t)(uint32_t)me.z * (W * PACK_STRIDE));
-            const ulonglong2 q0 = __ldg(q), q1 = __ldg(q + 1);
+            const ulonglong2 q0 = __ldg(reinterpret_cast<const ulonglong2 *>(a.packed + (size_t)(uint32_t)me.z * (a.words * PACK_STRIDE)));
             c.set(q0.x, q0.y, a.k);
-            valid = (q1.y & 1ull) != 0;
         }
-        unsigned long long dupc = 0;                        // duplicates per ring, XFIELD bits each
-        if (compare && __any_sync(0xffffffffu, valid)) {
-            uint32_t lo, span;
-            index_window((uint32_t)me.z, a.wlo, a.whi, lo, span);
-            const int gy = (me.y - a.g.min_y) >> CELL_SHIFT_Y;
-            bool pending = has;
-            for (;;) {
-                const int g = __reduce_min_sync(0xffffffffu, pending ? gy : INT_MAX);
-                if (g == INT_MAX) break;
-                const bool active = pending && gy == g;
-                pending = pending && !active;
-                if (!__any_sync(0xffffffffu, active && valid)) continue;
-                int row0;
-                const XRuns r = warp_runs(a.g, active, me.x, me.y, row0);
-                const int thr = (active && valid) ? a.e : -1;          // idle lanes never pass
-                // Chunks of 32 candidates are aligned so that the warp's own records -- consecutive in
-                // the run of grid row g -- are candidates 0..31 of ONE chunk, lane l's own record being
-                // candidate l there: v_own = position of this lane's record in the list
-                const int first = __ffs(__ballot_sync(0xffffffffu, active)) - 1;
-                const int gi = g - row0;                               // 0..2: the run of the centres' own grid row
-                int v_own = (int)(p - (gi == 0 ? r.start[0] : gi == 1 ? r.start[1] : r.start[2]));
-                if (gi >= 1) v_own += (int)r.len[0];
-                if (gi >= 2) v_own += (int)r.len[1];
-                const int v_warp = __shfl_sync(0xffffffffu, v_own - lane, first);    // may be negative
-                const int total = (int)r.total;
-                int v_first = (v_warp % 32 + 32) % 32;                 // first chunk: partly before the list unless aligned
-                if (v_first > 0) v_first -= 32;
-                for (int v0 = v_first; v0 < total; v0 += 32) {
-                    const int v = v0 + lane;
-                    __syncwarp();
-                    // outside the list: a pattern that is at least unlikely to pass (the exact path checks the range)
-                    s_pre[warp][lane] = (v >= 0 && v < total) ? __ldg(a.pre + r.record((uint32_t)v))
-                                                              : make_uint2(0x99999999u, 0x3c3c3c3cu);
-                    __syncwarp();
-                    uint32_t pass = 0;
-                    if (v0 == v_warp) {
-                        // own chunk: every lane's own record passes; collect the bit mask and drop it
+        const int gy = (me.y - a.g.min_y) >> CELL_SHIFT_Y;
+        bool pending = has;
+        for (;;) {                                          // one round per grid row the warp's centres sit in
+            const int g = __reduce_min_sync(0xffffffffu, pending ? gy : INT_MAX);
+            if (g == INT_MAX) break;
+            const bool active = pending && gy == g;
+            pending = pending && !active;
+            const int first = __ffs(__ballot_sync(0xffffffffu, active)) - 1;
+            const int xmin = __reduce_min_sync(0xffffffffu, active ? me.x : INT_MAX);
+            const int xmax = __reduce_max_sync(0xffffffffu, active ? me.x : INT_MIN);
+            const int ymax = __reduce_max_sync(0xffffffffu, active ? me.y : INT_MIN);
+            const int x0 = max(xmin - RING_RADIUS - a.g.min_x, 0) >> CELL_SHIFT_X;
+            const int x1 = min((xmax + RING_RADIUS - a.g.min_x) >> CELL_SHIFT_X, a.g.grid_w - 1);
+            const int y1 = min((ymax + RING_RADIUS - a.g.min_y) >> CELL_SHIFT_Y, a.g.grid_h - 1);
+            // run A: own grid row from the first active lane's record on; run B: the next grid row
+            const uint32_t j0 = p0 + (uint32_t)first;
+            const int len_a = (int)(__ldg(a.g.cell_start + (uint32_t)g * a.g.grid_w + x1 + 1) - j0);
+            uint32_t start_b = 0;
+            int len_b = 0;
+            if (g + 1 <= y1) {
+                start_b = __ldg(a.g.cell_start + (uint32_t)(g + 1) * a.g.grid_w + x0);
+                len_b = (int)(__ldg(a.g.cell_start + (uint32_t)(g + 1) * a.g.grid_w + x1 + 1) - start_b);
+            }
+            const int total = len_a + len_b;
+            const int need = active ? need_all : 33;                   // idle lanes never pass
+            // candidate record v of the list; beyond it a pattern that is at least unlikely to pass (the
+            // range is checked before a pair is queued)
+            auto fetch = [&](int v) {
+                return v < total ? __ldg(a.pre + (v < len_a ? j0 + (uint32_t)v : start_b + (uint32_t)(v - len_a)))
+                                 : make_uint2(0x99999999u, 0x3c3c3c3cu);
+            };
+            uint2 next = fetch(lane);
+            for (int v0 = 0; v0 < total; v0 += 32) {
+                __syncwarp();
+                s_pre[warp][lane] = next;
+                __syncwarp();
+                next = fetch(v0 + 32 + lane);                          // in flight while this chunk is tested
+                uint32_t pass = 0;
+                if (v0 == 0) {
+                    // the warp's own records are candidates 0.. of this chunk (lane l's is l - first): collect
+                    // the bit mask and keep only the records after one's own
 #pragma unroll
-                        for (int k = 0; k < 32; ++k)
-                            if ((int)__popc(c.unmatched(s_pre[warp][k].x, s_pre[warp][k].y)) <= thr) pass |= 1u << k;
-                        pass &= ~(1u << lane);
-                    } else {
-                        int best = 64;
+                    for (int k = 0; k < 32; ++k)
+                        if ((int)__popc(c.matched(s_pre[warp][k].x, s_pre[warp][k].y)) >= need) pass |= 1u << k;
+                    pass &= ~((2u << ((lane - first) & 31)) - 1u);
+                } else {
+                    int best = 0;
 #pragma unroll
-                        for (int k = 0; k < 32; k += 2)
-                            best = __vimin3_s32(best, (int)__popc(c.unmatched(s_pre[warp][k].x, s_pre[warp][k].y)),
-                                                (int)__popc(c.unmatched(s_pre[warp][k + 1].x, s_pre[warp][k + 1].y)));
-                        if (best <= thr) {
-                            for (int k = 0; k < 32; ++k)
-                                if ((int)__popc(c.unmatched(s_pre[warp][k].x, s_pre[warp][k].y)) <= thr) pass |= 1u << k;
-                        }
+                    for (int k = 0; k < 32; k += 2)
+                        best = __vimax3_s32(best, (int)__popc(c.matched(s_pre[warp][k].x, s_pre[warp][k].y)),
+                                            (int)__popc(c.matched(s_pre[warp][k + 1].x, s_pre[warp][k + 1].y)));
+                    // some candidate passed for these lanes (about one chunk in twenty): the warp finds out
+                    // which, one such lane at a time -- its sets broadcast, every lane tests one candidate
+                    uint32_t flagged = __ballot_sync(0xffffffffu, best >= need);
+                    while (flagged) {
+                        const int src = __ffs(flagged) - 1;
+                        flagged &= flagged - 1;
+                        Head32Sets o;
+                        o.sa = __shfl_sync(0xffffffffu, c.sa, src);
+                        o.sc = __shfl_sync(0xffffffffu, c.sc, src);
+                        o.sg = __shfl_sync(0xffffffffu, c.sg, src);
+                        o.st = __shfl_sync(0xffffffffu, c.st, src);
+                        const uint2 b = s_pre[warp][lane];
+                        const uint32_t hits = __ballot_sync(0xffffffffu, (int)__popc(o.matched(b.x, b.y)) >= need_all);
+                        if (lane == src) pass = hits;
                     }
-                    // exact path: padding, wells outside the rings or the index window drop out here
-                    while (pass) {
-                        const int k = __ffs(pass) - 1;
-                        pass &= pass - 1;
-                        const int vk = v0 + k;
-                        if (vk < 0 || vk >= total) continue;
-                        const uint32_t j = r.record((uint32_t)vk);
-                        if (j == p) continue;
-                        const int4 w = __ldg(a.g.cell_wells + j);
-                        const int dx = w.x - me.x, dy = w.y - me.y;
-                        const int d2 = dx * dx + dy * dy;
-                        if (!in_rings(d2, d2_max) || (uint32_t)((uint32_t)w.z - lo) > span) continue;
-                        PSeq<W> cs, bs;
-                        load_packed<W>(a.packed + (size_t)(uint32_t)me.z * (W * PACK_STRIDE), cs);
-                        load_packed<W>(a.packed + (size_t)(uint32_t)w.z * (W * PACK_STRIDE), bs);
-                        if (is_duplicate<W>(cs, bs, a.len, a.e, ham)) dupc += 1ull << (XFIELD * ring_of(d2));
-                    }
+                }
+                // pairs that passed go to the verify kernel (ring test, index windows, full-length compare)
+                while (pass) {
+                    const int k = __ffs(pass) - 1;
+                    pass &= pass - 1;
+                    const int vk = v0 + k;
+                    if (vk >= total) continue;
+                    const uint32_t j = vk < len_a ? j0 + (uint32_t)vk : start_b + (uint32_t)(vk - len_a);
+                    const uint32_t pos = atomicAdd(a.work_count, 1u);
+                    if (pos < a.work_cap) a.work[pos] = make_uint2(p, j);
                 }
             }
         }
-        // the sums of output_writer (count_well_duplicates.py:77-106), warp-reduced
-        const unsigned long long rl = (has && valid) ? __ldg(a.ringlen + p) : 0ull;
-        if (valid && a.e >= a.len && a.e >= 0) dupc = rl;
-        uint32_t hit_mask = 0;
+    }
+}
+
+// ============================================================================
+// per tile: exact test of the queued pairs, one pair per thread
+// ============================================================================
+struct XVerArgs {
+    XGrid g;
+    const uint64_t *packed;
+    unsigned long long *tally;           // [n] grid order
+    const uint2 *work;
+    const uint32_t *work_count;
+    uint32_t work_cap;
+    int levels, len, e, hamming;
+    uint32_t wlo, whi;
+};
+
+template <int W>
+__global__ void __launch_bounds__(256)
+exh_verify_kernel(XVerArgs a) {
+    const uint32_t n_work = min(__ldg(a.work_count), a.work_cap);
+    const int d2_max = c_x_d2[a.levels];
+    for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < n_work; i += gridDim.x * blockDim.x) {
+        const uint2 pr = __ldg(a.work + i);
+        const int4 me = __ldg(a.g.cell_wells + pr.x), w = __ldg(a.g.cell_wells + pr.y);
+        const int dx = w.x - me.x, dy = w.y - me.y;
+        const int d2 = dx * dx + dy * dy;
+        if (!in_rings(d2, d2_max)) continue;
+        // the scan window of the reference is not symmetric: each well of the pair has its own
+        uint32_t lo, span, lo2, span2;
+        index_window((uint32_t)me.z, a.wlo, a.whi, lo, span);
+        index_window((uint32_t)w.z, a.wlo, a.whi, lo2, span2);
+        const bool mine = (uint32_t)((uint32_t)w.z - lo) <= span;          // w is in me's window
+        const bool theirs = (uint32_t)((uint32_t)me.z - lo2) <= span2;     // me is in w's window
+        if (!mine && !theirs) continue;
+        PSeq<W> cs, bs;
+        load_packed<W>(a.packed + (size_t)(uint32_t)me.z * (W * PACK_STRIDE), cs);
+        load_packed<W>(a.packed + (size_t)(uint32_t)w.z * (W * PACK_STRIDE), bs);
+        if (is_duplicate<W>(cs, bs, a.len, a.e, a.hamming != 0)) {
+            const unsigned long long one = 1ull << (XFIELD * ring_of(d2));
+            if (mine) atomicAdd(a.tally + pr.x, one);
+            if (theirs) atomicAdd(a.tally + pr.y, one);
+        }
+    }
+}
+
+template <int W>
+static void launch_verify(const XVerArgs &a, unsigned blocks, cudaStream_t st) {
+    exh_verify_kernel<W><<<blocks, 256, 0, st>>>(a);
+}
+
+// ============================================================================
+// per tile: the sums of output_writer (count_well_duplicates.py:77-106)
+// ============================================================================
+__global__ void __launch_bounds__(256)
+exh_finish_kernel(const unsigned long long *__restrict__ tally, const unsigned long long *__restrict__ ringlen,
+                  uint32_t n, int L, int all_dups, unsigned long long *__restrict__ counters) {
+    __shared__ uint32_t s_cnt[1 + 5 * 5];
+    for (int i = threadIdx.x; i < 1 + 5 * 5; i += blockDim.x) s_cnt[i] = 0;
+    __syncthreads();
+    // per-thread sums over the grid-stride loop (ring sizes <= 4095 each, so 2^20 wells per thread fit 32 bits)
+    uint32_t targets = 0, wells[5], dups[5], hit[5], acco[5], acci[5];
 #pragma unroll
-        for (int l = 0; l < 5; ++l)
-            if (l < L && ((dupc >> (XFIELD * l)) & XFIELD_MAX)) hit_mask |= 1u << l;
-        const uint32_t n_valid = __popc(__ballot_sync(0xffffffffu, valid));
-        if (n_valid == 0) continue;
-        if (lane == 0) atomicAdd(&s_cnt[0], n_valid);
+    for (int l = 0; l < 5; ++l) wells[l] = dups[l] = hit[l] = acco[l] = acci[l] = 0;
+    const uint32_t stride = gridDim.x * blockDim.x;
+    for (uint32_t p0 = blockIdx.x * blockDim.x + threadIdx.x; p0 < n; p0 += 4 * stride) {
+        unsigned long long tt[4], rr[4];
 #pragma unroll
-        for (int l = 0; l < 5; ++l) {
-            if (l < L) {
-                const uint32_t wells = __reduce_add_sync(0xffffffffu, (uint32_t)(rl >> (XFIELD * l)) & XFIELD_MAX);
-                const uint32_t dups = __reduce_add_sync(0xffffffffu, (uint32_t)(dupc >> (XFIELD * l)) & XFIELD_MAX);
-                const uint32_t hit = __popc(__ballot_sync(0xffffffffu, (hit_mask >> l) & 1u));
-                const uint32_t acco = __popc(__ballot_sync(0xffffffffu, (hit_mask & ((2u << l) - 1u)) != 0));
-                const uint32_t acci = __popc(__ballot_sync(0xffffffffu, (hit_mask >> l) != 0));
-                if (lane == 0) {
-                    uint32_t *cc = s_cnt + 1 + 5 * l;
-                    atomicAdd(cc + 0, wells);
-                    if (dups) atomicAdd(cc + 1, dups);
-                    if (hit) atomicAdd(cc + 2, hit);
-                    if (acco) atomicAdd(cc + 3, acco);
-                    if (acci) atomicAdd(cc + 4, acci);
+        for (int u = 0; u < 4; ++u) {                       // eight loads in flight per thread
+            const uint32_t p = p0 + u * stride;
+            tt[u] = p < n ? __ldg(tally + p) : X_INVALID;
+            rr[u] = p < n ? __ldg(ringlen + p) : 0ull;
+        }
+#pragma unroll
+        for (int u = 0; u < 4; ++u) {
+            unsigned long long t = tt[u];
+            if (t & X_INVALID) continue;
+            const unsigned long long rl = rr[u];
+            if (all_dups) t = rl;                           // e >= len: every ring well is a duplicate
+            uint32_t hit_mask = 0;
+#pragma unroll
+            for (int l = 0; l < 5; ++l)
+                if (l < L && ((t >> (XFIELD * l)) & XFIELD_MAX)) hit_mask |= 1u << l;
+            targets++;
+#pragma unroll
+            for (int l = 0; l < 5; ++l) {
+                if (l < L) {
+                    wells[l] += (uint32_t)(rl >> (XFIELD * l)) & XFIELD_MAX;
+                    dups[l] += (uint32_t)(t >> (XFIELD * l)) & XFIELD_MAX;
+                    hit[l] += (hit_mask >> l) & 1u;
+                    // AccO: a hit at this ring or further in; AccI: at this ring or further out
+                    acco[l] += (hit_mask & ((2u << l) - 1u)) != 0;
+                    acci[l] += (hit_mask >> l) != 0;
                 }
+            }
+        }
+    }
+    const int lane = threadIdx.x & 31;
+    targets = __reduce_add_sync(0xffffffffu, targets);
+    if (lane == 0 && targets) atomicAdd(&s_cnt[0], targets);
+#pragma unroll
+    for (int l = 0; l < 5; ++l) {
+        if (l < L) {
+            const uint32_t v[5] = {__reduce_add_sync(0xffffffffu, wells[l]), __reduce_add_sync(0xffffffffu, dups[l]),
+                                   __reduce_add_sync(0xffffffffu, hit[l]), __reduce_add_sync(0xffffffffu, acco[l]),
+                                   __reduce_add_sync(0xffffffffu, acci[l])};
+            if (lane == 0) {
+#pragma unroll
+                for (int k = 0; k < 5; ++k)
+                    if (v[k]) atomicAdd(&s_cnt[1 + 5 * l + k], v[k]);
             }
         }
     }
     __syncthreads();
     for (int i = threadIdx.x; i < 1 + 5 * L; i += blockDim.x)
-        if (s_cnt[i]) atomicAdd(a.counters + i, (unsigned long long)s_cnt[i]);
-}
-
-template <int W>
-static void launch_compare(const XCmpArgs &a, unsigned blocks, cudaStream_t st) {
-    exh_compare_kernel<W><<<blocks, XW * 32, 0, st>>>(a);
+        if (s_cnt[i]) atomicAdd(counters + i, (unsigned long long)s_cnt[i]);
 }
 
 static XGrid make_grid(wd_ctx *ctx) {
@@ -387,34 +473,59 @@ int count_exhaustive(wd_ctx *ctx, int slot, const int32_t *order, int seq_len, i
     cudaStream_t st = ctx->stream;
     const size_t width = 1 + 5 * (size_t)levels;
     WD_TRY(ctx->x_pre.reserve((size_t)s.n * 8));
-    WD_TRY(ctx->x_counts.reserve(width * 8));
-    WD_CUDA(cudaMemsetAsync(ctx->x_counts.p, 0, width * 8, st));
-    exh_prefix_kernel<<<(s.n + 255) / 256, 256, 0, st>>>(ctx->cell_wells.as<int4>(), ctx->x_packed.as<uint64_t>(), words, s.n,
-                                                          ctx->x_pre.as<uint2>());
-    ctx->launches++;
-    XCmpArgs a;
-    a.g = make_grid(ctx);
-    a.pre = ctx->x_pre.as<uint2>();
-    a.packed = ctx->x_packed.as<uint64_t>();
-    a.ringlen = ctx->x_ringlen.as<unsigned long long>();
-    a.counters = ctx->x_counts.as<unsigned long long>();
-    a.levels = levels; a.len = seq_len; a.e = e; a.hamming = hamming;
-    a.k = head32_k(e, hamming != 0);
-    a.wlo = wlo; a.whi = whi;
-    // one warp per 32 centres; a few waves of CTAs per SM so that the tail is short
-    const unsigned blocks = (unsigned)std::min<size_t>(((size_t)s.n + XW * 32 - 1) / (XW * 32), (size_t)ctx->sm_count * 64);
-    switch (words) {
-        case 1: launch_compare<1>(a, blocks, st); break;
-        case 2: launch_compare<2>(a, blocks, st); break;
-        case 4: launch_compare<4>(a, blocks, st); break;
-        case 8: launch_compare<8>(a, blocks, st); break;
-        default: launch_compare<16>(a, blocks, st); break;
+    WD_TRY(ctx->x_tally.reserve((size_t)s.n * 8));
+    WD_TRY(ctx->x_counts.reserve(width * 8 + 8));
+    if (ctx->x_work_cap == 0) ctx->x_work_cap = std::max<size_t>((size_t)1 << 20, (size_t)s.n / 4);
+    std::vector<unsigned long long> h(width + 1);
+    for (int attempt = 0;; ++attempt) {
+        WD_TRY(ctx->x_work.reserve(ctx->x_work_cap * 8));
+        WD_CUDA(cudaMemsetAsync(ctx->x_counts.p, 0, width * 8 + 8, st));
+        uint32_t *work_count = reinterpret_cast<uint32_t *>(ctx->x_counts.as<unsigned long long>() + width);
+        exh_prefix_kernel<<<(s.n + 255) / 256, 256, 0, st>>>(ctx->cell_wells.as<int4>(), ctx->x_packed.as<uint64_t>(), words,
+                                                              s.n, ctx->x_pre.as<uint2>(), ctx->x_tally.as<unsigned long long>());
+        ctx->launches++;
+        // e < 0: no pair is a duplicate; e >= len: every pair is one -- neither needs a sequence
+        if (e >= 0 && e < seq_len) {
+            XCmpArgs a;
+            a.g = make_grid(ctx);
+            a.pre = ctx->x_pre.as<uint2>();
+            a.packed = ctx->x_packed.as<uint64_t>();
+            a.work = ctx->x_work.as<uint2>();
+            a.work_count = work_count;
+            a.work_cap = (uint32_t)std::min<size_t>(ctx->x_work_cap, 0xffffffffu);
+            a.words = words; a.e = e;
+            a.k = head32_k(e, hamming != 0);
+            // one warp per 32 centres; many short CTAs per SM so that the tail is short
+            const unsigned blocks = (unsigned)std::min<size_t>(((size_t)s.n + XW * 32 - 1) / (XW * 32), (size_t)ctx->sm_count * 64);
+            exh_compare_kernel<<<blocks, XW * 32, 0, st>>>(a);
+            ctx->launches++;
+            XVerArgs v;
+            v.g = a.g; v.packed = a.packed; v.tally = ctx->x_tally.as<unsigned long long>();
+            v.work = a.work; v.work_count = work_count; v.work_cap = a.work_cap;
+            v.levels = levels; v.len = seq_len; v.e = e; v.hamming = hamming; v.wlo = wlo; v.whi = whi;
+            const unsigned vblocks = (unsigned)ctx->sm_count * 2;
+            switch (words) {
+                case 1: launch_verify<1>(v, vblocks, st); break;
+                case 2: launch_verify<2>(v, vblocks, st); break;
+                case 4: launch_verify<4>(v, vblocks, st); break;
+                case 8: launch_verify<8>(v, vblocks, st); break;
+                default: launch_verify<16>(v, vblocks, st); break;
+            }
+            ctx->launches++;
+        }
+        exh_finish_kernel<<<(unsigned)std::min<size_t>(((size_t)s.n + 255) / 256, (size_t)ctx->sm_count * 8), 256, 0, st>>>(
+            ctx->x_tally.as<unsigned long long>(), ctx->x_ringlen.as<unsigned long long>(), s.n, levels,
+            (e >= 0 && e >= seq_len) ? 1 : 0, ctx->x_counts.as<unsigned long long>());
+        ctx->launches++;
+        WD_CUDA(cudaGetLastError());
+        WD_CUDA(cudaMemcpyAsync(h.data(), ctx->x_counts.p, (width + 1) * 8, cudaMemcpyDeviceToHost, st));
+        WD_CUDA(cudaStreamSynchronize(st));
+        const size_t queued = (size_t)(h[width] & 0xffffffffull);
+        if (queued <= ctx->x_work_cap) break;
+        // more pairs passed the 32-symbol test than the queue holds (low-complexity reads): grow it and redo the tile
+        if (attempt > 0) WD_FAIL(WD_E_CAPACITY, "wd_count_exhaustive: pair queue overflow (%zu pairs)", queued);
+        ctx->x_work_cap = queued + queued / 8 + 1024;
     }
-    ctx->launches++;
-    WD_CUDA(cudaGetLastError());
-    std::vector<unsigned long long> h(width);
-    WD_CUDA(cudaMemcpyAsync(h.data(), ctx->x_counts.p, width * 8, cudaMemcpyDeviceToHost, st));
-    WD_CUDA(cudaStreamSynchronize(st));
     for (size_t i = 0; i < width; ++i) tile_counters[i] = (int64_t)h[i];
     return WD_OK;
 }

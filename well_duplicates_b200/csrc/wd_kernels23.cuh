@@ -111,6 +111,85 @@ gather_pack_kernel(const TileDesc *__restrict__ descs, const uint32_t *__restric
     store_packed<W>(packed + ((size_t)blockIdx.y * n_slots + s) * (size_t)(W * PACK_STRIDE), q, meta);
 }
 
+// dense flavour (exhaustive mode): every well of the tile in index order, BCL
+// planes only.  One thread packs four consecutive wells from 32-bit plane loads
+// (a warp reads 128 contiguous bytes of a plane per instruction), 16 loads in
+// flight.  The four calls of a word are decoded together, byte-sliced:
+//   bit0 of the bases   v & 0x01010101
+//   bit1                (v >> 1) & 0x01010101
+//   no-call (byte == 0) ~(((v & 0x7f7f7f7f) + 0x7f7f7f7f) | v) >> 7 & 0x01010101   (exact, no cross-byte carry)
+// and cycle j of a group of eight lands at bit j of each byte by one multiply-add
+// (the integer FMA pipe: the logic pipe is the busy one); a 4 x 4 byte transpose
+// (PRMT) then turns four groups into one 32-bit run of symbols per well.
+__device__ __forceinline__ void transpose4x4_bytes(const uint32_t (&a)[4], uint32_t (&out)[4]) {
+    const uint32_t t0 = __byte_perm(a[0], a[1], 0x5140), t1 = __byte_perm(a[0], a[1], 0x7362);
+    const uint32_t u0 = __byte_perm(a[2], a[3], 0x5140), u1 = __byte_perm(a[2], a[3], 0x7362);
+    out[0] = __byte_perm(t0, u0, 0x5410);
+    out[1] = __byte_perm(t0, u0, 0x7632);
+    out[2] = __byte_perm(t1, u1, 0x5410);
+    out[3] = __byte_perm(t1, u1, 0x7632);
+}
+
+template <int W>
+__global__ void __launch_bounds__(256)
+dense_pack_bcl_kernel(const TileDesc *__restrict__ descs, uint32_t n, const unsigned long long *__restrict__ g_off,
+                      const uint8_t *__restrict__ g_kind, int len, uint64_t *__restrict__ packed) {
+    __shared__ unsigned long long s_off[MAX_ORDER];
+    __shared__ uint8_t s_kind[MAX_ORDER];
+    load_order(g_off, g_kind, len, s_off, s_kind);
+    const uint32_t w0 = (blockIdx.x * blockDim.x + threadIdx.x) * 4u;
+    if (w0 >= n) return;
+    const TileDesc d = descs[blockIdx.y];
+    const uint8_t *src = d.planes + w0;              // planes are padded to a multiple of 256 bytes: 4-byte loads stay inside
+    uint64_t *dst = packed + ((size_t)blockIdx.y * n + w0) * (size_t)(W * PACK_STRIDE);
+    uint32_t pf = 0;                                 // bit 8 i = PF of well i
+#pragma unroll
+    for (int i = 0; i < 4; ++i)
+        if (w0 + i < n) pf |= (uint32_t)(__ldg(d.filter + w0 + i) & 1u) << (8 * i);
+#pragma unroll 1
+    for (int w = 0; w < W; ++w) {
+        uint32_t lo[2][4], hi[2][4], nn[2][4];       // [half of the 64-symbol word][well]
+#pragma unroll
+        for (int half = 0; half < 2; ++half) {
+            uint32_t gl[4], gh[4], gn[4];            // one group of eight cycles each, byte i = well i
+#pragma unroll
+            for (int g2 = 0; g2 < 4; g2 += 2) {
+                const int p0 = 64 * w + 32 * half + 8 * g2;
+                uint32_t v[16];
+#pragma unroll
+                for (int j = 0; j < 16; ++j) {
+                    v[j] = 0x04040404u;              // beyond the sequence: no bit in any plane
+                    if (p0 + j < len) v[j] = __ldg(reinterpret_cast<const uint32_t *>(src + s_off[p0 + j]));
+                }
+#pragma unroll
+                for (int gg = 0; gg < 2; ++gg) {
+                    uint32_t al = 0, ah = 0, an = 0;
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        const uint32_t x = v[8 * gg + j];
+                        const uint32_t z = ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x);
+                        al += (x & 0x01010101u) * (1u << j);
+                        ah += ((x >> 1) & 0x01010101u) * (1u << j);
+                        an += ((z >> 7) & 0x01010101u) * (1u << j);
+                    }
+                    gl[g2 + gg] = al; gh[g2 + gg] = ah; gn[g2 + gg] = an;
+                }
+            }
+            transpose4x4_bytes(gl, lo[half]);
+            transpose4x4_bytes(gh, hi[half]);
+            transpose4x4_bytes(gn, nn[half]);
+        }
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+            if (w0 + i < n) {
+                ulonglong2 *q = reinterpret_cast<ulonglong2 *>(dst + ((size_t)i * W + w) * PACK_STRIDE);
+                q[0] = make_ulonglong2((uint64_t)lo[0][i] | ((uint64_t)lo[1][i] << 32), (uint64_t)hi[0][i] | ((uint64_t)hi[1][i] << 32));
+                q[1] = make_ulonglong2((uint64_t)nn[0][i] | ((uint64_t)nn[1][i] << 32), w == 0 ? (uint64_t)((pf >> (8 * i)) & 1u) : 0ull);
+            }
+        }
+    }
+}
+
 // packed -> one byte per symbol (0..3 ACGT, 4 N) for wd_get_seqs
 template <int W>
 __global__ void __launch_bounds__(256)
@@ -427,8 +506,13 @@ void launch_gather(wd_ctx *ctx, const TileDesc *descs, const uint32_t *slot_well
                           int len, uint64_t *packed) {
     const unsigned long long *g_off = ctx->order_dev.as<unsigned long long>();
     const uint8_t *g_kind = ctx->order_dev.as<uint8_t>() + (size_t)MAX_ORDER * 8;
-    dim3 grid((n_slots + 255) / 256, n_tiles);
-    gather_pack_kernel<W, ALL_BCL><<<grid, 256, 0, ctx->stream>>>(descs, slot_well, n_slots, g_off, g_kind, len, packed);
+    if (ALL_BCL && slot_well == nullptr) {
+        dim3 grid((n_slots + 1023) / 1024, n_tiles);
+        dense_pack_bcl_kernel<W><<<grid, 256, 0, ctx->stream>>>(descs, n_slots, g_off, g_kind, len, packed);
+    } else {
+        dim3 grid((n_slots + 255) / 256, n_tiles);
+        gather_pack_kernel<W, ALL_BCL><<<grid, 256, 0, ctx->stream>>>(descs, slot_well, n_slots, g_off, g_kind, len, packed);
+    }
     ctx->launches++;
 }
 

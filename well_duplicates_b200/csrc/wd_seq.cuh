@@ -349,11 +349,13 @@ struct Head32Sets {
         }
     }
     // blo, bhi: base planes of b's first 32 symbols
-    WD_HD uint32_t unmatched(uint32_t blo, uint32_t bhi) const {
+    // positions of b that find a partner (three 3-input logic ops; the complement would cost a fourth)
+    WD_HD uint32_t matched(uint32_t blo, uint32_t bhi) const {
         const uint32_t t0 = (blo & sc) | (~blo & sa);
         const uint32_t t1 = (blo & st) | (~blo & sg);
-        return ~((bhi & t1) | (~bhi & t0));
+        return (bhi & t1) | (~bhi & t0);
     }
+    WD_HD uint32_t unmatched(uint32_t blo, uint32_t bhi) const { return ~matched(blo, bhi); }
 };
 
 // k of the test above for (e, metric): Levenshtein <= 1 <=> Hamming <= 1 on equal lengths
