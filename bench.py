@@ -61,6 +61,7 @@ def parse():
                          "host memory (wd_tile_map_host) and the kernel pulls the sectors it needs over PCIe")
     ap.add_argument("--cpu-tiles", type=int, default=0, help="tiles in the cpu_baseline sample (0 = 24 per core)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-inflate", action="store_true", help="skip the host gunzip measurement (reported beside the metric)")
     ap.add_argument("--hamming", action="store_true")
     ap.add_argument("--zc-blocks", type=int, default=0,
                     help="distinct pinned host blocks for the zero-copy e2e (0 = one per tile slot if the host can pin them)")
@@ -182,6 +183,41 @@ def cpu_baseline_sample(planes_by_tile, filts, centres, offs, idx, n_tiles, thre
     dt = time.perf_counter() - t0
     wells = int(sum(int(r[1::5].sum()) for r in res))
     return dt, wells, res
+
+
+def host_inflate_sample(plane, threads, seconds=4.0):
+    """Gunzip stays on the host (BASELINE.json north_star) and is reported beside the metric: zlib inflate of
+    .bcl.gz-shaped members (one compressed plane of the benchmark tile) on all host threads."""
+    import zlib
+    raw = struct_header(plane.size) + plane.tobytes()
+    comp = zlib.compress(raw, 1)
+    comp = b"\x1f\x8b\x08\x00\x00\x00\x00\x00\x00\x03" + comp[2:-4] + struct_pack_tail(raw)
+
+    def one(_):
+        return len(zlib.decompressobj(wbits=31).decompress(comp))
+    one(0)
+    t0 = time.perf_counter()
+    done = 0
+    with ThreadPoolExecutor(max_workers=threads) as pool:
+        while time.perf_counter() - t0 < seconds:
+            done += sum(pool.map(one, range(threads)))
+    dt = time.perf_counter() - t0
+    return {"gb_per_s": done / dt / 1e9, "threads": threads, "seconds": dt, "compression_ratio": len(comp) / len(raw),
+            "lane_seconds": TILES_PER_LANE * N_CYCLES * (N_WELLS + 4) / (done / dt),
+            "note": "zlib inflate of gzip members shaped like one .bcl.gz plane of the benchmark tile (level 1), one member "
+                    "per host thread at a time; lane_seconds = the 96 x 50 planes of one lane at that rate. Outside value "
+                    "and e2e, which start from inflated planes in pinned host memory"}
+
+
+def struct_header(n):
+    import struct
+    return struct.pack("<I", n)
+
+
+def struct_pack_tail(raw):
+    import struct
+    import zlib
+    return struct.pack("<II", zlib.crc32(raw) & 0xffffffff, len(raw) & 0xffffffff)
 
 
 def run_reference(args, rank, world):
@@ -469,6 +505,13 @@ def main():
                          "traffic": traffic, "peak_source": "MEASURED_PEAKS.json (%s)" % peak_kind,
                          "kernel": "fused_count_kernel" if args.mode == 0 else "gather_pack_kernel+compare_count_kernel",
                          "algorithmic_bytes_per_launch": int(alg_bytes),
+                         "algorithmic_bytes_note": "SURVEY 8(d) / DESIGN 4.3: every 32-byte sector that holds a well of a "
+                                                   "pass-filter target, in all %d planes, + filter, index and counter bytes. "
+                                                   "The kernel stops reading a well as soon as its prefix proves dist > e, so "
+                                                   "it moves fewer bytes than that (traffic); dram_achieved / dram_frac are "
+                                                   "the rate at which it really drives HBM" % N_CYCLES,
+                         "dram_achieved": None if not traffic else traffic * (n_tiles / TILES_PER_LANE) / (ms_per_step / 1e3) / 1e9,
+                         "dram_frac": None if not traffic else traffic * (n_tiles / TILES_PER_LANE) / (ms_per_step / 1e3) / 1e9 / peak,
                          "distinct_32B_sectors_per_plane_per_tile": int(np.mean([p[1] for p in per_tile])),
                          "note": "duration = CUDA events around %d launches on the launching stream; at N>1 it also "
                                  "covers the publish kernel and the all-reduce" % args.steps},
@@ -512,6 +555,8 @@ def main():
                                     "matches_gpu_counters": bool(ok),
                                     "sample": "%d tiles of the same lane (one per host thread), planes already gunzipped "
                                               "in RAM; C restatement of the reference (oracle/welldup_oracle.c)" % n_cpu}
+        if not args.no_inflate and world == 1:
+            line["host_inflate"] = host_inflate_sample(pins[0].array[0], os.cpu_count() or 1)
         print(json.dumps(line))
     if world > 1:
         dist.barrier()

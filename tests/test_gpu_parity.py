@@ -593,3 +593,36 @@ def test_flowcell_driver_single_rank(name):
     with contextlib.redirect_stdout(out):
         flowcell.main(argv)
     assert out.getvalue() == want
+
+
+# ------------------------------------------------------- whole-run workflow --
+def test_workflow_whole_run(tmp_path):
+    """python -m well_duplicates_b200.workflow RUN WORKDIR: the per-lane files are
+    what the count command prints for the flags Snakefile.count_dups:153-160
+    derives from RunInfo.xml, the summary is their ``tail`` (:146-151)."""
+    import shutil
+    import subprocess
+    from well_duplicates_b200 import count_cli, workflow
+    run = tmp_path / "run"
+    run.mkdir()
+    os.symlink(os.path.join(GOLDEN, "run_bcl", "Data"), run / "Data")
+    (run / "RunInfo.xml").write_text(
+        '<RunInfo><Run><Reads><Read Number="1" NumCycles="14"/></Reads><FlowcellLayout><TileSet><Tiles>'
+        '<Tile>2_1101</Tile><Tile>1_1103</Tile><Tile>2_1103</Tile><Tile>1_1102</Tile></Tiles></TileSet>'
+        '</FlowcellLayout></Run></RunInfo>')
+    work = tmp_path / "work"
+    work.mkdir()
+    shutil.copy(os.path.join(GOLDEN, "locs", "hex_small_n40_s13.list"), work / "40clusters.list")
+    err = io.StringIO()
+    with contextlib.redirect_stderr(err):
+        workflow.main([str(run), str(work), "-n", "40", "--read-length", "13"])
+    names = ["40targets_lane1.txt", "40targets_lane2.txt"]
+    for lane, name in zip("12", names):
+        out = io.StringIO()
+        with contextlib.redirect_stdout(out), contextlib.redirect_stderr(io.StringIO()):
+            count_cli.main(["-f", str(work / "40clusters.list"), "-n", "40", "-s", "1103", "-r", str(run), "-i", lane,
+                            "-l", "5", "--cycles", "0-13"])
+        assert (work / name).read_text() == out.getvalue()
+        assert "Lane: %s\tTile: 1103" % lane in out.getvalue() or "1103" in out.getvalue()
+    want = subprocess.run(["tail", "-n", "6"] + names, capture_output=True, text=True, cwd=work).stdout
+    assert (work / "40targets_all_lanes.txt").read_text() == want
