@@ -114,8 +114,10 @@ def config3(eng, args):
     t = out["levenshtein"]["ms"] / 1e3
     return {"config": "3: exhaustive mode, one full-size tile (%d wells), every well a target out to ring 5, 50 cycles" % N,
             **out, "algorithmic_bytes": alg, "achieved_gb_per_s": alg / t / 1e9, "hbm_peak_gb_per_s": peak(),
-            "bound_note": "388 M ordered pairs need a ring test (~1.8 G candidate tests) and a sequence compare each: "
-                          "the kernel is bound by instruction issue, not by HBM (see DESIGN.md)",
+            "bound_note": "whole wd_count_exhaustive call (dense pack, prefix layout, compare, verify, finish; ring sizes are "
+                          "cached per .locs). 935 M candidate pairs get a 32-symbol set test of 3 LOP3 + POPC each: the "
+                          "compare kernel is bound by integer issue (logic pipe 84 %, POPC pipe 76 % busy), not by HBM "
+                          "(DESIGN.md 4.5)",
             "cpu_port_s_scaled": t_cpu * N / n_c, "cpu_sample": "first %d rows (%d wells) of the tile, C restatement, 1 thread, "
             "scaled by wells" % (rows, n_c), "cropped_tile_matches_oracle": bool(np.array_equal(got, want))}
 
