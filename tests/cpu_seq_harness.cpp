@@ -72,8 +72,15 @@ static void prefix_dp(const uint8_t *a, const uint8_t *b, int len, int k, int ch
             const int upto = known + chunk < len ? known + chunk : len;
             for (; known < upto; ++known) wd::pseq_set<W>(pa, known, a[known]);
         }
-        wd::pdp_step<W>(s, pa, known, len, p, k, b[p]);
-        out[p + 1] = wd::pdp_band_min<W>(s, len, p + 1, k);
+        // the kernel's dispatch: rounds inside the first 32 rows take the word-0 forms
+        if (wd::pdp_round_in_word0(p, 1, k)) {
+            wd::pdp_step_word0<W>(s, (uint32_t)pa.lo[0], (uint32_t)pa.hi[0], (uint32_t)pa.nn[0], wd::len_mask32(known, 0), b[p]);
+            out[p + 1] = wd::pdp_band_min_word0<W>(s, len, p + 1, k);
+            if (out[p + 1] != wd::pdp_band_min<W>(s, len, p + 1, k)) out[p + 1] = -1000;     // the two forms must agree
+        } else {
+            wd::pdp_step<W>(s, pa, known, len, p, k, b[p]);
+            out[p + 1] = wd::pdp_band_min<W>(s, len, p + 1, k);
+        }
     }
 }
 

@@ -223,7 +223,7 @@ struct CountArgs {
     unsigned long long dup_cap;
     uint32_t t, n_slots;
     int levels, len, e, hamming;
-    int step0, step1;                // fused kernel: cycles read per round (first, later), 1..16
+    int step0, step1;                // fused kernel: cycles read per round (first, later), 1..8
     int cchunk;                      // fused kernel: centre cycles decoded per warp-wide load (8, 16 or 32)
     int n_head;                      // fused kernel: positions 0..n_head-1 are read from the tile's head planes in HBM
 };
@@ -394,6 +394,15 @@ __device__ __forceinline__ bool ring_round(const TileDesc &d, uint32_t well, int
         mism += __popc((bits_at<W>(c.lo, p, n) ^ glo) | (bits_at<W>(c.hi, p, n) ^ ghi) | (bits_at<W>(c.nn, p, n) ^ gnn));
         return mism <= e;
     }
+    if (pdp_round_in_word0(p, n, k)) {
+        // the first round of every well: only word 0 of the programme is active (wd_seq.cuh)
+        const uint32_t alo = (uint32_t)c.lo[0], ahi = (uint32_t)c.hi[0], ann = (uint32_t)c.nn[0];
+        const uint32_t amask = len_mask32(known_c, 0);
+#pragma unroll
+        for (int j = 0; j < NMAX; ++j)
+            if (j < n) pdp_step_word0<W>(dp, alo, ahi, ann, amask, call_symbol(raw[j]));
+        return pdp_band_min_word0<W>(dp, len, p + n, k) <= e;
+    }
 #pragma unroll
     for (int j = 0; j < NMAX; ++j)
         if (j < n) pdp_step<W>(dp, c, known_c, len, p + j, k, call_symbol(raw[j]));
@@ -479,8 +488,9 @@ fused_count_kernel(CountArgs a) {
                     }
                     // ---- ring wells: lane = well ---------------------------------------------
                     if (alive) {
-                        if (n > 8) alive = ring_round<W, ALL_BCL, 16>(d, well, rank, s_off, s_kind, c, known_c, len, p, n, k, e, ham_like, dp, mism);
-                        else if (n > 4) alive = ring_round<W, ALL_BCL, 8>(d, well, rank, s_off, s_kind, c, known_c, len, p, n, k, e, ham_like, dp, mism);
+                        // three sizes of round are compiled (the schedules that win use 8 + 2 or 8 + 4): a
+                        // smaller kernel, fewer instruction-cache misses
+                        if (n > 4) alive = ring_round<W, ALL_BCL, 8>(d, well, rank, s_off, s_kind, c, known_c, len, p, n, k, e, ham_like, dp, mism);
                         else if (n > 2) alive = ring_round<W, ALL_BCL, 4>(d, well, rank, s_off, s_kind, c, known_c, len, p, n, k, e, ham_like, dp, mism);
                         else alive = ring_round<W, ALL_BCL, 2>(d, well, rank, s_off, s_kind, c, known_c, len, p, n, k, e, ham_like, dp, mism);
                     }

@@ -325,6 +325,50 @@ WD_HD int pdp_band_min(const PrefixDP<W> &s, int len, int p, int k) {
     return best;
 }
 
+// The same two operations for the rounds whose band lies inside the first 32
+// rows (p + n + k + 1 <= 32 for a round of n symbols starting at p): only word
+// 0 of the vectors is active, row 0 always enters with +1, and the word-select
+// loops and their branches of the general form fall away -- a third of the
+// instructions.  This is the first round of every ring well, i.e. nearly all
+// the symbols the fused kernel ever feeds.  Bit-identical to the general form
+// (tests/test_seq_predicates_cpu.py drives both through the same dispatch).
+WD_HD bool pdp_round_in_word0(int p, int n, int k) { return p + n + k + 1 <= 32; }
+
+// alo/ahi/ann: word 0 of a's planes; amask: rows of word 0 that are known (len_mask32(known_a, 0))
+template <int W>
+WD_HD void pdp_step_word0(PrefixDP<W> &s, uint32_t alo, uint32_t ahi, uint32_t ann, uint32_t amask, unsigned c) {
+    const uint32_t tlo = (c & 1u) ? ~0u : 0u;
+    const uint32_t thi = (c & 2u) ? ~0u : 0u;
+    const uint32_t tn = (c & 4u) ? ~0u : 0u;
+    const uint32_t tany = c <= 4u ? ~0u : 0u;
+    const uint32_t Eq = ~((alo ^ tlo) | (ahi ^ thi) | (ann ^ tn)) & amask & tany;
+    const uint32_t pv = s.Pv[0], mv = s.Mv[0];
+    const uint32_t Xv = Eq | mv;
+    const uint32_t Xh = (((Eq & pv) + pv) ^ pv) | Eq;
+    const uint32_t Ph = ((mv | ~(Xh | pv)) << 1) | 1u;          // row 0: D[0][p+1] - D[0][p] = +1
+    const uint32_t Mh = (pv & Xh) << 1;
+    s.Pv[0] = Mh | ~(Xv | Ph);
+    s.Mv[0] = Ph & Xv;
+}
+
+// pdp_band_min for p + k <= 32 (all rows of the band in word 0)
+template <int W>
+WD_HD int pdp_band_min_word0(const PrefixDP<W> &s, int len, int p, int k) {
+    const int jlo = p - k > 0 ? p - k : 0;
+    const int jhi = p + k < len ? p + k : len;
+    const uint32_t below = jlo >= 32 ? ~0u : ((1u << jlo) - 1u);
+    const uint32_t pv = s.Pv[0], mv = s.Mv[0];
+    int d = p + popc32(pv & below) - popc32(mv & below);
+    int best = d + (p - jlo);
+    for (int j = jlo; j < jhi; ++j) {             // row j -> j + 1 is bit j
+        d += (int)((pv >> j) & 1u) - (int)((mv >> j) & 1u);
+        const int off = j + 1 - p;
+        const int v = d + (off < 0 ? -off : off);
+        best = v < best ? v : best;
+    }
+    return best;
+}
+
 // Cheap necessary condition for dist(a, b) <= e from the first 32 symbols of b
 // (exhaustive mode, wd_exhaustive.cu), on the lo/hi planes only: N aliases to A,
 // so every true match stays a match and the count of unmatched positions can

@@ -323,7 +323,7 @@ int count_async(wd_ctx *ctx, int first_slot, int n_tiles, const int32_t *order, 
     // (wd_tile_map_host) are bound by the number of sector requests -> many short rounds
     const bool over_pcie = ctx->slots[first_slot].mapped != nullptr;
     a.step0 = over_pcie ? 4 : 8;
-    a.step1 = over_pcie ? 1 : 2;
+    a.step1 = over_pcie ? 1 : 4;
     a.cchunk = over_pcie ? 8 : 16;
     if (const char *cc = getenv("WELLDUP_CENTRE_CHUNK")) {
         const int v = atoi(cc);
@@ -331,7 +331,7 @@ int count_async(wd_ctx *ctx, int first_slot, int n_tiles, const int32_t *order, 
     }
     if (const char *sch = getenv("WELLDUP_STEPS")) {
         int s0 = 0, s1 = 0;
-        if (sscanf(sch, "%d,%d", &s0, &s1) == 2 && s0 >= 1 && s0 <= 16 && s1 >= 1 && s1 <= 16) {
+        if (sscanf(sch, "%d,%d", &s0, &s1) == 2 && s0 >= 1 && s0 <= 8 && s1 >= 1 && s1 <= 8) {
             a.step0 = s0;
             a.step1 = s1;
         }
@@ -364,7 +364,7 @@ int count_async(wd_ctx *ctx, int first_slot, int n_tiles, const int32_t *order, 
         int n_head = 2, n_groups = 16;              // profiles/r01_notes.md: sweep on the B200 box
         if (const char *hp = getenv("WELLDUP_HEAD_PLANES")) n_head = atoi(hp);
         if (const char *hg = getenv("WELLDUP_HEAD_GROUPS")) n_groups = atoi(hg);
-        n_head = std::max(0, std::min(n_head, std::min(seq_len, 16)));
+        n_head = std::max(0, std::min(n_head, std::min(seq_len, 8)));
         for (int k = 0; k < n_tiles; ++k)
             if (ctx->slots[first_slot + k].mapped == nullptr)
                 WD_FAIL(WD_E_ARG, "wd_count: host-mapped and staged tile slots cannot share one call");
