@@ -133,7 +133,6 @@ struct wd_ctx {
     wd::DevBuf gs_idx, gs_packed, gs_codes;
     // exhaustive mode (wd_exhaustive.cu)
     wd::DevBuf x_packed, x_counts, x_pre, x_ringlen, x_flags, x_tally, x_work;
-    bool dense_tma = true;            // dense pack: stage planes with TMA bulk copies (planes in HBM)
     size_t x_work_cap = 0;            // pairs the queue between exh_compare_kernel and exh_verify_kernel holds
     int x_geom_levels = 0;            // ring sizes in x_ringlen are valid for (levels, window); 0 = none
     uint32_t x_geom_wlo = 0, x_geom_whi = 0, x_geom_first_empty = 0;

@@ -190,109 +190,6 @@ dense_pack_bcl_kernel(const TileDesc *__restrict__ descs, uint32_t n, const unsi
     }
 }
 
-// The same pass with the planes staged by the TMA engine (planes resident in
-// HBM): a CTA owns 1024 consecutive wells; one elected thread issues bulk copies
-// (cp.async.bulk, 1 KB per plane, eight planes per stage, four stages = 32 KB of
-// shared memory) that complete on an mbarrier each, the 256 threads consume a
-// stage with conflict-free 32-bit shared-memory loads while the next three are
-// in flight.  No register is tied up by a load in flight and the memory system
-// sees 1 KB requests instead of 128-byte ones.
-constexpr int DPT_WELLS = 1024;          // wells per CTA (256 threads x 4)
-constexpr int DPT_PLANES = 8;            // planes per stage (one group of eight cycles)
-constexpr int DPT_STAGES = 4;
-
-__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
-    uint32_t ok;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
-    } while (!ok);
-}
-
-template <int W>
-__global__ void __launch_bounds__(256)
-dense_pack_bcl_tma_kernel(const TileDesc *__restrict__ descs, uint32_t n, const unsigned long long *__restrict__ g_off,
-                          const uint8_t *__restrict__ g_kind, int len, uint64_t *__restrict__ packed) {
-    __shared__ __align__(128) uint8_t s_buf[DPT_STAGES][DPT_PLANES][DPT_WELLS];
-    __shared__ __align__(8) uint64_t s_bar[DPT_STAGES];
-    __shared__ unsigned long long s_off[MAX_ORDER];
-    __shared__ uint8_t s_kind[MAX_ORDER];
-    load_order(g_off, g_kind, len, s_off, s_kind);
-    const TileDesc d = descs[blockIdx.y];
-    const uint32_t b0 = blockIdx.x * DPT_WELLS;
-    const uint32_t w0 = b0 + threadIdx.x * 4u;
-    // bytes of a plane this CTA copies: planes are padded to a multiple of 256 bytes
-    const uint32_t cb = (uint32_t)min((unsigned long long)DPT_WELLS, d.stride - b0);
-    const int n_groups = (len + DPT_PLANES - 1) / DPT_PLANES;
-    if (threadIdx.x == 0) {
-        for (int i = 0; i < DPT_STAGES; ++i)
-            asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" :: "r"(smem_u32(&s_bar[i])) : "memory");
-        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-    __syncthreads();
-    auto issue = [&](int g) {                        // one thread: the planes of group g into stage g % DPT_STAGES
-        const int stage = g % DPT_STAGES;
-        const int np = min(DPT_PLANES, len - g * DPT_PLANES);
-        const uint32_t bar = smem_u32(&s_bar[stage]);
-        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(cb * (uint32_t)np) : "memory");
-        for (int j = 0; j < np; ++j)
-            asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
-                         :: "r"(smem_u32(&s_buf[stage][j][0])), "l"(d.planes + s_off[g * DPT_PLANES + j] + b0), "r"(cb), "r"(bar)
-                         : "memory");
-    };
-    if (threadIdx.x == 0)
-        for (int g = 0; g < min(n_groups, DPT_STAGES); ++g) issue(g);
-    uint32_t pf = 0;                                 // bit 8 i = PF of well i
-#pragma unroll
-    for (int i = 0; i < 4; ++i)
-        if (w0 + i < n) pf |= (uint32_t)(__ldg(d.filter + w0 + i) & 1u) << (8 * i);
-    uint64_t *dst = packed + ((size_t)blockIdx.y * n + w0) * (size_t)(W * PACK_STRIDE);
-#pragma unroll 1
-    for (int w = 0; w < W; ++w) {
-        uint32_t lo[2][4], hi[2][4], nn[2][4];       // [half of the 64-symbol word][well]
-#pragma unroll
-        for (int half = 0; half < 2; ++half) {
-            uint32_t gl[4], gh[4], gn[4];            // one group of eight cycles each, byte i = well i
-#pragma unroll
-            for (int gi = 0; gi < 4; ++gi) {
-                const int g = 8 * w + 4 * half + gi;
-                uint32_t al = 0, ah = 0, an = 0;
-                if (g < n_groups) {                  // uniform over the CTA
-                    const int stage = g % DPT_STAGES;
-                    mbar_wait(smem_u32(&s_bar[stage]), (uint32_t)(g / DPT_STAGES) & 1u);
-                    const int np = min(DPT_PLANES, len - g * DPT_PLANES);
-#pragma unroll
-                    for (int j = 0; j < DPT_PLANES; ++j) {
-                        if (j < np) {
-                            const uint32_t x = *reinterpret_cast<const uint32_t *>(&s_buf[stage][j][threadIdx.x * 4]);
-                            const uint32_t z = ~(((x & 0x7f7f7f7fu) + 0x7f7f7f7fu) | x);
-                            al += (x & 0x01010101u) * (1u << j);
-                            ah += ((x >> 1) & 0x01010101u) * (1u << j);
-                            an += ((z >> 7) & 0x01010101u) * (1u << j);
-                        }
-                    }
-                    __syncthreads();                 // the stage has been read by everybody: refill it
-                    if (threadIdx.x == 0 && g + DPT_STAGES < n_groups) issue(g + DPT_STAGES);
-                }
-                gl[gi] = al; gh[gi] = ah; gn[gi] = an;
-            }
-            transpose4x4_bytes(gl, lo[half]);
-            transpose4x4_bytes(gh, hi[half]);
-            transpose4x4_bytes(gn, nn[half]);
-        }
-#pragma unroll
-        for (int i = 0; i < 4; ++i) {
-            if (w0 + i < n) {
-                ulonglong2 *q = reinterpret_cast<ulonglong2 *>(dst + ((size_t)i * W + w) * PACK_STRIDE);
-                q[0] = make_ulonglong2((uint64_t)lo[0][i] | ((uint64_t)lo[1][i] << 32), (uint64_t)hi[0][i] | ((uint64_t)hi[1][i] << 32));
-                q[1] = make_ulonglong2((uint64_t)nn[0][i] | ((uint64_t)nn[1][i] << 32), w == 0 ? (uint64_t)((pf >> (8 * i)) & 1u) : 0ull);
-            }
-        }
-    }
-}
-
 // packed -> one byte per symbol (0..3 ACGT, 4 N) for wd_get_seqs
 template <int W>
 __global__ void __launch_bounds__(256)
@@ -621,9 +518,7 @@ void launch_gather(wd_ctx *ctx, const TileDesc *descs, const uint32_t *slot_well
     const uint8_t *g_kind = ctx->order_dev.as<uint8_t>() + (size_t)MAX_ORDER * 8;
     if (ALL_BCL && slot_well == nullptr) {
         dim3 grid((n_slots + 1023) / 1024, n_tiles);
-        // planes in HBM: staged by TMA bulk copies; planes left in pinned host memory: plain loads
-        if (ctx->dense_tma) dense_pack_bcl_tma_kernel<W><<<grid, 256, 0, ctx->stream>>>(descs, n_slots, g_off, g_kind, len, packed);
-        else dense_pack_bcl_kernel<W><<<grid, 256, 0, ctx->stream>>>(descs, n_slots, g_off, g_kind, len, packed);
+        dense_pack_bcl_kernel<W><<<grid, 256, 0, ctx->stream>>>(descs, n_slots, g_off, g_kind, len, packed);
     } else {
         dim3 grid((n_slots + 255) / 256, n_tiles);
         gather_pack_kernel<W, ALL_BCL><<<grid, 256, 0, ctx->stream>>>(descs, slot_well, n_slots, g_off, g_kind, len, packed);

@@ -465,7 +465,6 @@ int pack_dense(wd_ctx *ctx, int slot, const int32_t *order, int seq_len, int *wo
     WD_TRY(upload_descs(ctx, slot, 1));
     const int words = words_for(seq_len);
     WD_TRY(ctx->x_packed.reserve((size_t)s.n * words * PACK_STRIDE * 8));
-    ctx->dense_tma = s.mapped == nullptr && getenv("WELLDUP_NO_TMA") == nullptr;
     launch_gather_any(ctx, words, all_bcl, ctx->descs.as<TileDesc>(), nullptr, s.n, 1, seq_len, ctx->x_packed.as<uint64_t>());
     WD_CUDA(cudaGetLastError());
     *words_out = words;
