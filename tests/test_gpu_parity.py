@@ -578,6 +578,41 @@ def test_full_tile_monotone_in_e(eng, full_tile):
         prev = pt[0][:, 1::2]
 
 
+def test_full_tile_exhaustive_properties(eng, full_tile):
+    """Exhaustive mode at BASELINE size (every one of the 4 309 650 wells a target):
+    properties that do not need an oracle run of that size."""
+    X, Y, td, centres, offs, idx = full_tile
+    order = list(range(50))
+    lev = eng.count_exhaustive(0, order, 5, 2, False)
+    assert np.array_equal(lev, eng.count_exhaustive(0, order, 5, 2, False))          # idempotent (tallies are reset)
+    ham = eng.count_exhaustive(0, order, 5, 2, True)
+    n_pf = int((td.filt & 1).sum())
+    assert lev[0] == ham[0] == n_pf                                                  # centre PF rule
+    assert np.array_equal(lev[1::5], ham[1::5])                                      # Wells are geometry only
+    assert np.all(lev[2::5] >= ham[2::5]) and lev[2::5].sum() > ham[2::5].sum()      # Lev <= Ham, planted shifts differ
+    assert lev[4 + 5 * 4] == lev[5]                                                  # AccO[5] == AccI[1] == any hit
+    assert np.all(np.diff(lev[4::5]) >= 0) and np.all(np.diff(lev[5::5]) <= 0)       # AccO grows outwards, AccI inwards
+    # interior wells of the lattice have 6 k wells in ring k: the mean ring size sits just below that
+    assert np.all(lev[1::5] <= 6 * np.arange(1, 6) * n_pf) and np.all(lev[1::5] >= 5.9 * np.arange(1, 6) * n_pf)
+    # fewer levels: the same inner rings
+    l3 = eng.count_exhaustive(0, order, 3, 2, False)
+    assert l3[0] == lev[0]
+    for k in (1, 2, 3, 4):                                                           # Wells, Dups, Hit, AccO of rings 1..3
+        assert np.array_equal(l3[k::5], lev[k::5][:3])
+    # the 2500 sampled targets are a subset: their duplicates cannot exceed the exhaustive totals
+    _, c = eng.count(0, 1, order, 2, False, mode=0, per_target=False)
+    assert np.all(c[0][2::5] <= lev[2::5]) and np.all(c[0][3::5] <= lev[3::5])
+    # no sequence decides: e >= len makes every ring well a duplicate, e < 0 none
+    every = eng.count_exhaustive(0, order, 5, 50, False)
+    assert np.array_equal(every[2::5], every[1::5]) and np.all(every[3::5] == n_pf) and np.all(every[4::5] == n_pf)
+    none = eng.count_exhaustive(0, order, 5, -1, False)
+    assert none[0] == n_pf and not none[2::5].any() and not none[3::5].any() and np.array_equal(none[1::5], lev[1::5])
+    # monotone in e
+    e1 = eng.count_exhaustive(0, order, 5, 1, False)
+    e3 = eng.count_exhaustive(0, order, 5, 3, False)
+    assert np.all(e1[2::5] <= lev[2::5]) and np.all(lev[2::5] <= e3[2::5])
+
+
 # ------------------------------------------------------------------ flowcell driver --
 @pytest.mark.parametrize("name", ["two_lanes", "lev_default", "cbcl_default", "summary"])
 def test_flowcell_driver_single_rank(name):
