@@ -258,6 +258,19 @@ def run_reference(args, rank, world):
     print(json.dumps(line))
 
 
+def _ranges(cpus):
+    out, start, prev = [], None, None
+    for c in cpus + [None]:
+        if start is None:
+            start = prev = c
+        elif c is not None and c == prev + 1:
+            prev = c
+        else:
+            out.append("%d" % start if start == prev else "%d-%d" % (start, prev))
+            start = prev = c
+    return ",".join(out)
+
+
 def workload_config(args, per_gpu_tiles):
     return {"workload": "hiseq4000_lane_per_gpu: %d tiles x %d wells, %d targets x %d rings, %d-cycle BCL substring, "
                         "%s e=%d" % (per_gpu_tiles, N_WELLS, N_TARGETS, LEVELS, N_CYCLES,
@@ -279,6 +292,12 @@ def main():
         run_reference(args, rank, world)
         return
 
+    # stdout carries ONE JSON line: native libraries write there too (NCCL prints its version banner on
+    # fd 1), so keep a private handle on the real stdout and point fd 1 at stderr for the rest of the run
+    sys.stdout.flush()
+    report = os.fdopen(os.dup(1), "w")
+    os.dup2(2, 1)
+
     import torch
     import torch.distributed as dist
 
@@ -287,6 +306,10 @@ def main():
 
     torch.cuda.set_device(local)
     if world > 1:
+        from well_duplicates_b200.engine import bind_to_gpu_numa_node
+        bound = None if os.environ.get("WELLDUP_NO_NUMA_BIND") else bind_to_gpu_numa_node(local)
+        sys.stderr.write("rank %d: GPU %d, host cores %s\n" % (rank, local, "unchanged" if bound is None else
+                                                               "%s (next to %s)" % (_ranges(bound[1]), bound[0])))
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     eng = Engine(local)
     l2_prev = eng.set_l2_fetch_granularity(args.l2_fetch) if args.l2_fetch else None
@@ -557,7 +580,8 @@ def main():
                                               "in RAM; C restatement of the reference (oracle/welldup_oracle.c)" % n_cpu}
         if not args.no_inflate and world == 1:
             line["host_inflate"] = host_inflate_sample(pins[0].array[0], os.cpu_count() or 1)
-        print(json.dumps(line))
+        report.write(json.dumps(line) + "\n")
+        report.flush()
     if world > 1:
         dist.barrier()
         dist.destroy_process_group()

@@ -21,6 +21,37 @@ def _c(a, dtype):
     return np.ascontiguousarray(a, dtype=dtype)
 
 
+def bind_to_gpu_numa_node(device):
+    """Multi-GPU boxes: run this process on the cores next to its GPU, so that the pinned staging memory
+    it allocates (first touch) sits on the NUMA node the GPU's PCIe link hangs off.  Eight ranks whose
+    staging memory ends up on one socket halve each other's host-to-device bandwidth.  Returns the PCI
+    address and the cores chosen, or None when the platform does not say (then nothing is changed)."""
+    import os
+    import subprocess
+    try:
+        out = subprocess.run(["nvidia-smi", "--query-gpu=pci.bus_id", "--format=csv,noheader", "-i", str(int(device))],
+                             capture_output=True, text=True, timeout=20).stdout.strip().splitlines()
+        bdf = out[0].strip().lower()
+        if bdf.count(":") == 2 and len(bdf.split(":")[0]) == 8:
+            bdf = bdf[4:]                                    # nvidia-smi prints an 8-digit domain, sysfs a 4-digit one
+        with open("/sys/bus/pci/devices/%s/local_cpulist" % bdf) as fh:
+            spec = fh.read().strip()
+        cpus = set()
+        for part in spec.split(","):
+            if "-" in part:
+                a, b = part.split("-")
+                cpus.update(range(int(a), int(b) + 1))
+            elif part:
+                cpus.add(int(part))
+        cpus &= os.sched_getaffinity(0)
+        if not cpus:
+            return None
+        os.sched_setaffinity(0, cpus)
+        return bdf, sorted(cpus)
+    except Exception:
+        return None
+
+
 class PinnedArray:
     """numpy view over page-locked host memory from wd_host_alloc."""
 

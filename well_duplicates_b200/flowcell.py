@@ -102,6 +102,9 @@ def main(argv=None):
         sys.stdout.flush()
         report_stream = os.fdopen(os.dup(1), "w")
         os.dup2(2, 1)
+    if world > 1:
+        from .engine import bind_to_gpu_numa_node
+        bind_to_gpu_numa_node(local)          # staging memory next to this rank's GPU
     if world > 1 and not dist.is_initialized():
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     say = (lambda *a: None) if (args.quiet or rank != 0) else count_cli.log
