@@ -405,6 +405,20 @@ def test_exhaustive_matches_reference_report(eng, oracle, case, tmp_path):
     assert report.format_report(case["lane"], xy.shape[0], case["tiles"], rows, o["levels"], verbose=True) == want
 
 
+@pytest.mark.parametrize("case", _exhaustive_manifest(), ids=lambda c: c["name"])
+def test_exhaustive_cli_matches_reference_report(case, tmp_path):
+    """count_well_duplicates.py --exhaustive-locs S_LOCS (an extension: no target file) prints what the
+    unmodified reference printed for a target file holding every well."""
+    from well_duplicates_b200 import count_cli
+    argv = ["--exhaustive-locs", locs_path(case["locs"], tmp_path), "-r", os.path.join(GOLDEN, "run_bcl"), "-s", "hiseq_x",
+            "-i", case["lane"], "-t", ",".join(case["tiles"]), "-q"] + case["args"]
+    out = io.StringIO()
+    with contextlib.redirect_stdout(out):
+        count_cli.main(argv)
+    with open(os.path.join(GOLDEN, "exhaustive", case["name"] + ".stdout")) as fh:
+        assert out.getvalue() == fh.read()
+
+
 @pytest.mark.parametrize("e,ham,levels", [(2, False, 5), (2, True, 5), (3, False, 2)])
 def test_exhaustive_medium_tile_vs_oracle(eng, oracle, e, ham, levels):
     """A cropped tile (150 rows x 300 wells, 50 cycles), every well a target,

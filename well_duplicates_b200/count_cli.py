@@ -28,7 +28,7 @@ def parse_args(argv=None):
     p = ArgumentParser(description="Counts well duplicates on a patterned flowcell without mapping: reads "
                                    "within LEVEL rings of each sampled well are compared with it.",
                        formatter_class=ArgumentDefaultsHelpFormatter)
-    p.add_argument("-f", "--coord_file", dest="coord_file", required=True, help="target list from prepare_cluster_indexes")
+    p.add_argument("-f", "--coord_file", dest="coord_file", help="target list from prepare_cluster_indexes")
     p.add_argument("-e", "--edit_distance", dest="edit_distance", type=int, default=2,
                    help="largest distance that still counts as a duplicate")
     p.add_argument("-n", "--sample_size", dest="sample_size", type=int, default=2500,
@@ -46,7 +46,14 @@ def parse_args(argv=None):
     p.add_argument("-S", "--summary-only", action="store_true", help="print only the per-lane summary")
     p.add_argument("-q", "--quiet", action="store_true", help="no log output")
     p.add_argument("--version", action="version", version=str(__VERSION__))
-    return p.parse_args(argv)
+    # extension (not in the reference): what "prepare_cluster_indexes.py -n <every well>" followed by this
+    # command would report, without the multi-gigabyte target file and its ~86 h of preparation per tile
+    p.add_argument("--exhaustive-locs", metavar="S_LOCS", help="every well of each tile is a target; rings come "
+                   "straight from this .locs file (replaces -f; -n is ignored)")
+    args = p.parse_args(argv)
+    if not args.coord_file and not args.exhaustive_locs:
+        p.error("the following arguments are required: -f/--coord_file")
+    return args
 
 
 def expected_tiles(stype, tile_id=None):
@@ -81,8 +88,34 @@ def parse_cycles(args):
     return [(args.start, args.end)]
 
 
+def main_exhaustive(args):
+    """--exhaustive-locs: wd_count_exhaustive per tile, same report."""
+    from .prepare_cli import read_locs
+    from .report import write_report
+    say = (lambda *a: None) if args.quiet else log
+    lanes = args.lane.split(",") if args.lane else range(1, 8 + 1)
+    tiles = expected_tiles(args.stype, args.tile_id)
+    wanted = [c for s, e in parse_cycles(args) for c in range(s, e)]
+    bcl_reader = bcl_direct_reader.BCLReader(args.run)
+    eng = bcl_reader.engine
+    _, xy = read_locs(args.exhaustive_locs)
+    eng.load_locs(xy)
+    pool = ThreadPoolExecutor(max_workers=8)
+    for lane in lanes:
+        rows = []
+        for tile in tiles:
+            say("Reading tile %s in lane %s" % (tile, lane))
+            plane_of = bcl_reader.get_tile(lane, tile).stage(0, wanted, pool)
+            rows.append(eng.count_exhaustive(0, [plane_of[c] for c in wanted], args.level, args.edit_distance, args.hamming))
+        order = sorted(range(len(tiles)), key=lambda k: tiles[k])
+        write_report(sys.stdout, lane, xy.shape[0], [tiles[k] for k in order], [rows[k] for k in order], args.level,
+                     verbose=not args.summary_only)
+
+
 def main(argv=None):
     args = parse_args(argv)
+    if args.exhaustive_locs:
+        return main_exhaustive(args)
     say = (lambda *a: None) if args.quiet else log
     lanes = args.lane.split(",") if args.lane else range(1, 8 + 1)
     tiles = expected_tiles(args.stype, args.tile_id)
