@@ -11,21 +11,25 @@
 //    LENGTH column of the reference, and its "Got no wells" RuntimeError,
 //    :70-76) and keeps them in HBM;
 //  * sequences change per tile.  A dense pass packs every well (coalesced plane
-//    reads, wd_stage23.cu), exh_prefix_kernel lays the first 32 symbols of
-//    every well out in GRID order (the order of stage 1's cell records), and
-//    exh_compare_kernel tests every centre against every well of the grid
-//    cells around it.
+//    reads, wd_kernels23.cuh), exh_prefix_kernel lays the first 32 symbols of
+//    every well out in GRID order (the order of stage 1's cell records) and
+//    resets the per-well tallies, exh_compare_kernel looks at every pair of
+//    wells that could be ring neighbours, exh_verify_kernel runs the exact test
+//    on the pairs that passed and exh_finish_kernel sums the tallies into the
+//    counters of the report.
 //
-// Both big kernels give one THREAD to each centre and one candidate list to
-// each WARP: the 32 centres of a warp are consecutive grid records (wells of
-// the same few cells), so one list -- the runs of records that cover all 32
-// neighbourhoods -- serves them all.  The warp stages 32 candidates at a time
-// in shared memory and every lane tests the same candidate against its own
-// centre (broadcast LDS, no divergence).  For the compare that test is a
-// 32-symbol necessary condition for dist <= e on two bit-planes (Head32Sets,
-// wd_seq.cuh: three LOP3 and a POPC) and only the pairs that pass -- real
-// duplicates, about one in 10^4 -- reach the exact path: ring test, index
-// window, full-length compare on the packed words.
+// The geometry and the compare kernel give one THREAD to each centre and one
+// candidate list to each WARP: the 32 centres of a warp are consecutive grid
+// records (wells of the same few cells), so one list -- runs of records that
+// cover all 32 neighbourhoods -- serves them all.  The warp stages 32
+// candidates at a time in shared memory and every lane tests the same
+// candidate against its own centre (broadcast LDS, no divergence).  For the
+// compare that test is a 32-symbol necessary condition for dist <= e on two
+// bit-planes (Head32Sets, wd_seq.cuh: three LOP3 and a POPC); distance and ring
+// are symmetric, so every unordered pair is looked at once and a duplicate is
+// credited to both wells.  Only the pairs that pass -- real duplicates, about
+// one in 10^4 -- are queued for the exact test: ring, both index windows,
+// full-length compare on the packed words, one pair per thread.
 #include <algorithm>
 #include <climits>
 #include <cstring>
