@@ -142,6 +142,9 @@ struct wd_ctx {
     uint32_t last_t = 0;
     bool last_per_target = false;
     size_t publish_n = 0;
+    std::vector<unsigned long long> order_off;   // plane order / kinds / tile descriptors as last uploaded
+    std::vector<uint8_t> order_kind, descs_host;
+    std::vector<int32_t> publish_map;   // tile_row ++ lane_row as last uploaded behind the publish buffer
     size_t dup_cap = 0;
     uint64_t last_h2d_bytes = 0;      // bytes the last wd_count copied to HBM itself (head planes of host-mapped tiles)
 };

@@ -87,6 +87,7 @@ int filter_rank(wd_ctx *ctx, const int *slot_ids, int n) {
 
 static TileDesc make_desc(const TileSlot &s) {
     TileDesc d;
+    memset(&d, 0, sizeof(d));                     // descriptors are compared bytewise (upload_descs)
     d.planes = s.mapped ? s.mapped : s.planes.as<uint8_t>();
     d.stride = s.stride;
     d.filter = s.mapped_filter ? s.mapped_filter : s.filter.as<uint8_t>();
@@ -174,10 +175,18 @@ static int prepare_order(wd_ctx *ctx, int first_slot, int n_tiles, const int32_t
                         order[p], first_slot);
     }
     cudaStream_t st = ctx->stream;
+    const void *before = ctx->order_dev.p;
     WD_TRY(ctx->order_dev.reserve((size_t)MAX_ORDER * 9));
-    WD_CUDA(cudaMemcpyAsync(ctx->order_dev.p, off.data(), (size_t)len * 8, cudaMemcpyHostToDevice, st));
-    WD_CUDA(cudaMemcpyAsync(ctx->order_dev.as<uint8_t>() + (size_t)MAX_ORDER * 8, kind.data(), (size_t)len,
-                            cudaMemcpyHostToDevice, st));
+    // a lane is counted with the same plane order call after call: upload it when it changes only (small
+    // pageable copies in front of a 0.4 ms kernel are not free)
+    if (ctx->order_dev.p != before || off != ctx->order_off || kind != ctx->order_kind) {
+        WD_CUDA(cudaMemcpyAsync(ctx->order_dev.p, off.data(), (size_t)len * 8, cudaMemcpyHostToDevice, st));
+        WD_CUDA(cudaMemcpyAsync(ctx->order_dev.as<uint8_t>() + (size_t)MAX_ORDER * 8, kind.data(), (size_t)len,
+                                cudaMemcpyHostToDevice, st));
+        WD_CUDA(cudaStreamSynchronize(st));          // the sources are pageable and local
+        ctx->order_off.swap(off);
+        ctx->order_kind.swap(kind);
+    }
     return WD_OK;
 }
 
@@ -193,8 +202,14 @@ int upload_descs(wd_ctx *ctx, int first_slot, int n_tiles) {
         }
         h[k] = make_desc(s);
     }
+    const void *before = ctx->descs.p;
     WD_TRY(ctx->descs.reserve((size_t)n_tiles * sizeof(TileDesc)));
-    WD_CUDA(cudaMemcpyAsync(ctx->descs.p, h.data(), (size_t)n_tiles * sizeof(TileDesc), cudaMemcpyHostToDevice, st));
+    const size_t bytes = (size_t)n_tiles * sizeof(TileDesc);
+    if (ctx->descs.p != before || ctx->descs_host.size() != bytes || memcmp(ctx->descs_host.data(), h.data(), bytes) != 0) {
+        WD_CUDA(cudaMemcpyAsync(ctx->descs.p, h.data(), bytes, cudaMemcpyHostToDevice, st));
+        WD_CUDA(cudaStreamSynchronize(st));          // `h` is pageable and local
+        ctx->descs_host.assign(reinterpret_cast<const uint8_t *>(h.data()), reinterpret_cast<const uint8_t *>(h.data()) + bytes);
+    }
     return WD_OK;
 }
 
@@ -441,11 +456,19 @@ int publish_counters(wd_ctx *ctx, const int32_t *tile_row, const int32_t *lane_r
             WD_FAIL(WD_E_ARG, "wd_publish_counters: row index out of range");
     cudaStream_t st = ctx->stream;
     const size_t n = (size_t)n_rows_total * width;
+    const void *before = ctx->publish.p;
     WD_TRY(ctx->publish.reserve(n * 8 + (size_t)n_tiles * 8));
     int32_t *rows = reinterpret_cast<int32_t *>(ctx->publish.as<unsigned long long>() + n);
     WD_CUDA(cudaMemsetAsync(ctx->publish.p, 0, n * 8, st));
-    WD_CUDA(cudaMemcpyAsync(rows, tile_row, (size_t)n_tiles * 4, cudaMemcpyHostToDevice, st));
-    WD_CUDA(cudaMemcpyAsync(rows + n_tiles, lane_row, (size_t)n_tiles * 4, cudaMemcpyHostToDevice, st));
+    // the row maps are the same step after step (a rank keeps its tiles): upload them when they change only --
+    // two small pageable copies cost more than the kernel they feed
+    std::vector<int32_t> map(tile_row, tile_row + n_tiles);
+    map.insert(map.end(), lane_row, lane_row + n_tiles);
+    if (ctx->publish.p != before || n != ctx->publish_n || map != ctx->publish_map) {
+        WD_CUDA(cudaMemcpyAsync(rows, map.data(), map.size() * 4, cudaMemcpyHostToDevice, st));
+        WD_CUDA(cudaStreamSynchronize(st));          // `map` is pageable and local
+        ctx->publish_map.swap(map);
+    }
     const int total = n_tiles * width;
     publish_kernel<<<(total + 255) / 256, 256, 0, st>>>(ctx->counters.as<unsigned long long>(), rows, rows + n_tiles,
                                                          n_tiles, width, ctx->publish.as<unsigned long long>());
