@@ -50,6 +50,10 @@ extern "C" {
 #define WD_E_CUDA (-4)     /* CUDA runtime failure */
 #define WD_E_ARG (-5)      /* ValueError: argument outside what the library supports */
 #define WD_E_CAPACITY (-6) /* caller's output array too small; required size is reported */
+#define WD_E_NOENT (-7)    /* FileNotFoundError: the reader then tries the CBCL file (bcl_direct_reader.py:209-216) */
+#define WD_E_IO (-8)       /* OSError: open / read failed */
+#define WD_E_EOF (-9)      /* EOFError: compressed data end before the end-of-stream marker (gzip.open().read()) */
+#define WD_E_DATA (-10)    /* gzip.BadGzipFile / zlib.error: not gzip, corrupt deflate data, CRC or length mismatch */
 
 #define WD_MAX_LEVELS 15   /* rings per target (the reference's MAX_DISTS gives 5) */
 #define WD_MAX_SEQ_LEN 1024 /* compared symbols per well (sum of all --cycles ranges) */
@@ -189,6 +193,37 @@ WD_API int wd_counters_devptr(wd_ctx *ctx, void **devptr, size_t *n_int64);
 WD_API int wd_count_exhaustive(wd_ctx *ctx, int tile_slot, const int32_t *plane_order, int seq_len,
                         int levels, uint32_t window_lo, uint32_t window_hi,
                         int edit_distance, int hamming, int64_t *tile_counters);
+
+/* ---- host staging: gunzip -----------------------------------------------------------
+ * Host-only (no GPU needed).  Replaces gzip.open(file).read() of the per-cycle
+ * .bcl.gz slurp (bcl_direct_reader.py:207-208, :333-345) and the seek + gzip
+ * member read of a CBCL tile block (:292-301): each job reads `size` bytes at
+ * `offset` of `path` (size 0 = to the end of the file) -- or takes src[0, size)
+ * when path is NULL -- and inflates every gzip member found there to dst, which
+ * may point into page-locked memory from wd_host_alloc() so that wd_tile_map_host
+ * can hand the planes to the kernels without another copy.  Jobs are independent
+ * and are spread over `threads` native threads (0 = one per hardware thread).
+ * gzip.open() semantics: CRC-32 and length of every member are checked, members
+ * may follow each other, zero padding after a member is skipped, an empty input
+ * gives no bytes.  Per-job status: WD_OK, WD_E_NOENT, WD_E_IO, WD_E_EOF,
+ * WD_E_DATA, WD_E_CAPACITY (more than dst_cap bytes), WD_E_ARG; the call returns
+ * the status of the first failed job (its message in wd_last_error()). */
+typedef struct wd_inflate_job {
+    const char *path;      /* file to read, or NULL */
+    const uint8_t *src;    /* compressed bytes when path is NULL */
+    uint64_t offset;       /* first byte of the gzip member(s) in the file */
+    uint64_t size;         /* compressed bytes (0 with a path = to the end of the file) */
+    uint8_t *dst;          /* where the inflated bytes go */
+    uint64_t dst_cap;      /* room at dst */
+    uint64_t out_len;      /* [out] bytes written to dst */
+    int32_t status;        /* [out] WD_OK or WD_E_* */
+    char message[220];     /* [out] text of the failure */
+} wd_inflate_job;
+WD_API int wd_inflate_batch(wd_inflate_job *jobs, size_t n_jobs, int threads);
+/* one buffer, calling thread */
+WD_API int wd_gunzip(const uint8_t *src, size_t n, uint8_t *dst, size_t cap, size_t *out_len);
+/* CRC-32 of RFC 1952 (zlib.crc32): running value in, running value out */
+WD_API uint32_t wd_crc32(uint32_t crc, const uint8_t *data, size_t n);
 
 #ifdef __cplusplus
 }

@@ -675,3 +675,73 @@ def test_workflow_whole_run(tmp_path):
         assert "1101" in out.getvalue()
     want = subprocess.run(["tail", "-n", "6"] + names, capture_output=True, text=True, cwd=work).stdout
     assert (work / "40targets_all_lanes.txt").read_text() == want
+
+
+def test_staging_pipeline_zero_copy_and_copied_equal_oracle(eng, oracle, tmp_path):
+    """staging.lane_batches: files -> page-locked block (native inflate threads) -> kernels.
+    Planes read in place across PCIe and planes copied from the block give the oracle's
+    counters, for BCL tiles of two sizes and a CBCL lane with both block kinds, whatever the
+    batch size; get_seqs through the same path equals the oracle's decode."""
+    R, CP = oracle
+    from well_duplicates_b200 import staging, synth
+    from well_duplicates_b200.reader import BCLReader
+    rng = np.random.default_rng(21)
+    run = str(tmp_path / "run")
+    row_len, ncyc = 120, 24
+    sizes = {1101: 20011, 1102: 20011, 1103: 26000, 1104: 26000, 1105: 26000}
+    data = {1: {}, 2: {}}
+    for tile, n in sizes.items():
+        data[1][tile] = synth.make_tile(rng, n, ncyc, row_len, pf_rate=0.7, dup_rate=0.25, shift_share=0.3, nocall_rate=0.01)
+        synth.write_bcl_tile(run, 1, tile, data[1][tile], compresslevel=int(rng.integers(1, 9)))
+    for tile in (1101, 2101, 1102):
+        data[2][tile] = synth.make_tile(rng, 20011, ncyc, row_len, pf_rate=0.6, dup_rate=0.25, shift_share=0.3)
+    synth.write_cbcl_lane(run, 2, data[2], excluded_from_cycle=9)
+    X, Y = synth.hex_lattice(20011, row_len)
+    centres = rng.choice(20011, size=500, replace=False).astype(np.uint32)
+    offs, idx = CP.rings_csr(X, Y, centres)
+    eng.load_targets(centres, offs, idx, 5)
+    wanted = list(range(3, 21)) + [1, 2]
+    rd = BCLReader(run, engine=eng)
+    st = staging.Stager(threads=4, cbcl_cache=rd._cbcl_cache)
+    pfm = {t: (td.filt & 1).astype(bool) for t, td in data[2].items()}
+
+    def oracle_rows(lane, tile):
+        td = data[lane][tile]
+        if lane == 1:
+            planes, kinds = [td.planes[c] for c in wanted], ["bcl"] * len(wanted)
+        else:
+            planes, kinds = [], []
+            for c in wanted:
+                nib = synth.bcl_to_nibbles(td.planes[c])
+                planes.append(synth.pack_nibbles(nib[pfm[tile]] if c >= 9 else nib))
+                kinds.append("cbcl_excl" if c >= 9 else "cbcl")
+        return CP.count_tile(planes, kinds, td.filt, centres, offs, idx, 5, 2, False)
+
+    for lane, names in ((1, list(sizes)), (2, [1101, 2101, 1102])):
+        want = {t: oracle_rows(lane, t) for t in names}
+        for per_batch in (None, 2, 1):
+            for zero_copy, mode in ((True, 0), (False, 0), (False, 1), (True, 1)):
+                seen = []
+                for got, batch in staging.lane_batches(st, lambda t: rd.get_tile(lane, t), names, wanted, per_batch=per_batch):
+                    plane_of = st.deliver(eng, batch, first_slot=0, zero_copy=zero_copy)
+                    pt, cnt = eng.count(0, len(got), [plane_of[c] for c in wanted], 2, False, mode=mode)
+                    for k, t in enumerate(got):
+                        assert np.array_equal(pt[k], want[t][0]) and np.array_equal(cnt[k], want[t][1]), (lane, t, per_batch, zero_copy, mode)
+                    seen += got
+                assert seen == names
+        # the reader API on top of the same staging: a few wells (sectors pulled in place) and many (planes copied)
+        t = names[-1]
+        td = data[lane][t]
+        for wells in (idx[:40], np.arange(0, 20011, 3)):
+            got = rd.get_tile(lane, t).get_seqs([int(w) for w in wells], 2, 20)
+            if lane == 1:
+                planes, kinds = [td.planes[c] for c in range(2, 20)], ["bcl"] * 18
+            else:
+                planes = [synth.pack_nibbles(synth.bcl_to_nibbles(td.planes[c])[pfm[t]] if c >= 9 else synth.bcl_to_nibbles(td.planes[c]))
+                          for c in range(2, 20)]
+                kinds = ["cbcl_excl" if c >= 9 else "cbcl" for c in range(2, 20)]
+            keys = sorted({int(w) for w in wells})
+            wcodes, wpf = CP.get_codes(planes, kinds, td.filt, np.array(keys))
+            assert [got[k][0] for k in keys] == ["".join("ACGTN"[c] for c in row) for row in wcodes]
+            assert [got[k][1] for k in keys] == [bool(f) for f in wpf]
+    st.close()

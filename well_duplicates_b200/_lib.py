@@ -3,6 +3,7 @@
 There is no CPU fallback: if the shared library has not been built, or no CUDA
 device is usable, the functions here raise."""
 import ctypes as C
+import gzip
 import os
 
 HERE = os.path.dirname(os.path.abspath(__file__))
@@ -10,6 +11,7 @@ LIB_PATH = os.path.join(HERE, "libwelldup.so")
 
 WD_OK = 0
 WD_E_INDEX, WD_E_RUNTIME, WD_E_ASSERT, WD_E_CUDA, WD_E_ARG, WD_E_CAPACITY = -1, -2, -3, -4, -5, -6
+WD_E_NOENT, WD_E_IO, WD_E_EOF, WD_E_DATA = -7, -8, -9, -10
 PLANE_EMPTY, PLANE_BCL, PLANE_CBCL, PLANE_CBCL_EXCL = 0, 1, 2, 3
 MAX_LEVELS = 15
 MAX_SEQ_LEN = 1024
@@ -23,8 +25,18 @@ class CapacityError(RuntimeError):
     """A caller-provided output array was too small (WD_E_CAPACITY)."""
 
 
+# the staging errors are the ones gzip.open(...).read() raises in the reference's reader
 _EXC = {WD_E_INDEX: IndexError, WD_E_RUNTIME: RuntimeError, WD_E_ASSERT: AssertionError,
-        WD_E_CUDA: CudaError, WD_E_ARG: ValueError, WD_E_CAPACITY: CapacityError}
+        WD_E_CUDA: CudaError, WD_E_ARG: ValueError, WD_E_CAPACITY: CapacityError,
+        WD_E_NOENT: FileNotFoundError, WD_E_IO: OSError, WD_E_EOF: EOFError, WD_E_DATA: gzip.BadGzipFile}
+
+
+class InflateJob(C.Structure):
+    """struct wd_inflate_job (include/welldup.h)."""
+    _fields_ = [("path", C.c_char_p), ("src", C.c_void_p), ("offset", C.c_uint64), ("size", C.c_uint64),
+                ("dst", C.c_void_p), ("dst_cap", C.c_uint64), ("out_len", C.c_uint64), ("status", C.c_int32),
+                ("message", C.c_char * 220)]
+
 
 _p = C.c_void_p
 _u8p, _i32p, _u32p, _i64p, _u64p, _f32p = (C.POINTER(t) for t in
@@ -59,6 +71,9 @@ SIGNATURES = {
     "wd_dup_pairs": (C.c_int, [_p, _p, C.c_size_t, _u64p]),
     "wd_publish_counters": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, C.POINTER(_p), C.POINTER(C.c_size_t)]),
     "wd_counters_devptr": (C.c_int, [_p, C.POINTER(_p), C.POINTER(C.c_size_t)]),
+    "wd_inflate_batch": (C.c_int, [C.POINTER(InflateJob), C.c_size_t, C.c_int]),
+    "wd_gunzip": (C.c_int, [_p, C.c_size_t, _p, C.c_size_t, C.POINTER(C.c_size_t)]),
+    "wd_crc32": (C.c_uint32, [C.c_uint32, _p, C.c_size_t]),
     "wd_count_exhaustive": (C.c_int, [_p, C.c_int, _p, C.c_int, C.c_int, C.c_uint32, C.c_uint32, C.c_int, C.c_int, _p]),
 }
 
@@ -84,8 +99,11 @@ def load():
     return lib
 
 
+def raise_status(rc, msg):
+    raise _EXC.get(rc, RuntimeError)(msg)
+
+
 def check(rc):
     if rc == WD_OK:
         return
-    msg = load().wd_last_error().decode("utf-8", "replace")
-    raise _EXC.get(rc, RuntimeError)(msg)
+    raise_status(rc, load().wd_last_error().decode("utf-8", "replace"))

@@ -6,8 +6,6 @@ the counter reduction run in the CUDA library."""
 import re
 import sys
 from argparse import ArgumentDefaultsHelpFormatter, ArgumentParser
-from concurrent.futures import ThreadPoolExecutor
-
 import numpy as np
 
 from . import reader as bcl_direct_reader
@@ -17,7 +15,7 @@ from .targets import load_targets
 __VERSION__ = 0.3
 HISEQ_4000 = "hiseq_4000"
 HISEQ_X = "hiseq_x"
-HBM_BUDGET_BYTES = 120 << 30     # planes kept resident per batch of tiles
+HBM_BUDGET_BYTES = 120 << 30     # planes kept resident per batch of tiles (flowcell driver, copy staging)
 
 
 def log(msg):
@@ -92,6 +90,7 @@ def main_exhaustive(args):
     """--exhaustive-locs: wd_count_exhaustive per tile, same report."""
     from .prepare_cli import read_locs
     from .report import write_report
+    from .staging import lane_batches
     say = (lambda *a: None) if args.quiet else log
     lanes = args.lane.split(",") if args.lane else range(1, 8 + 1)
     tiles = expected_tiles(args.stype, args.tile_id)
@@ -100,12 +99,14 @@ def main_exhaustive(args):
     eng = bcl_reader.engine
     _, xy = read_locs(args.exhaustive_locs)
     eng.load_locs(xy)
-    pool = ThreadPoolExecutor(max_workers=8)
+    stager = bcl_direct_reader.default_stager(bcl_reader._cbcl_cache)
     for lane in lanes:
         rows = []
-        for tile in tiles:
-            say("Reading tile %s in lane %s" % (tile, lane))
-            plane_of = bcl_reader.get_tile(lane, tile).stage(0, wanted, pool)
+        # the dense pack reads every byte of every plane: planes are copied to HBM (DMA from the
+        # pinned block) while the next tile inflates
+        for names, batch in lane_batches(stager, lambda t: bcl_reader.get_tile(lane, t), tiles, wanted, per_batch=1,
+                                         announce=lambda t: say("Reading tile %s in lane %s" % (t, lane))):
+            plane_of = stager.deliver(eng, batch, first_slot=0, zero_copy=False)
             rows.append(eng.count_exhaustive(0, [plane_of[c] for c in wanted], args.level, args.edit_distance, args.hamming))
         order = sorted(range(len(tiles)), key=lambda k: tiles[k])
         write_report(sys.stdout, lane, xy.shape[0], [tiles[k] for k in order], [rows[k] for k in order], args.level,
@@ -129,47 +130,35 @@ def main(argv=None):
     wanted = [c for s, e in cycles for c in range(s, e)]
     # the duplicate-pair log needs the two-pass kernels and per-tile ordering on stderr
     mode = 0 if args.quiet else 1
-    pool = ThreadPoolExecutor(max_workers=8)
+    from .staging import lane_batches
+    stager = bcl_direct_reader.default_stager(bcl_reader._cbcl_cache)
 
     for lane in lanes:
         lane_dupl = {}
-        batch = []      # (tile name, slot)
-
-        def flush():
-            if not batch:
-                return
-            per_target, _ = eng.count(0, len(batch), [plane_of[c] for c in wanted], args.edit_distance,
-                                      args.hamming, mode=mode, per_target=True)
+        # Files -> page-locked planes on native threads, one batch ahead of the GPU (staging.py).
+        # -q: many tiles per launch, planes stay in host memory and the fused kernel pulls the
+        # sectors it needs.  Otherwise one tile at a time, in the reference's log order, planes
+        # copied to HBM for the two-pass kernels that feed the duplicate-pair log.
+        for names, staged in lane_batches(stager, lambda t: bcl_reader.get_tile(lane, t), tiles, wanted,
+                                          per_batch=None if args.quiet else 1,
+                                          announce=lambda t: say("Reading tile %s in lane %s" % (t, lane))):
+            plane_of = stager.deliver(eng, staged, first_slot=0, zero_copy=args.quiet)
+            order = [plane_of[c] for c in wanted]
+            say("Got %i sequences from %i contiguous cycle ranges." % (n_unique * len(cycles), len(cycles)))
+            per_target, _ = eng.count(0, len(names), order, args.edit_distance, args.hamming, mode=mode, per_target=True)
             pairs = eng.dup_pairs() if mode == 1 else ()
-            for k, (tname, tile_obj) in enumerate(batch):
+            for k, tname in enumerate(names):
                 lane_dupl[tname] = dupl_from_per_target(per_target[k], args.level)
                 rows = [r for r in pairs if r[0] == k]
                 if rows:
                     wells = sorted({int(centres[r[1]]) for r in rows} | {int(r[2]) for r in rows})
-                    codes, _ = eng.get_seqs(k, wells, [plane_of[c] for c in wanted])
+                    codes, _ = eng.get_seqs(k, wells, order)
                     seq = dict(zip(wells, bcl_direct_reader.codes_to_strings(codes)))
                     for _, t_ord, well, dist in rows:
                         c = int(centres[t_ord])
                         say("center seq at {:>07}: {}".format(c, seq[c]))
                         say("well seq at   {:>07}: {}".format(int(well), seq[int(well)]))
                         say("edit distance: {}".format(int(dist)))
-            batch.clear()
-
-        per_batch = 1
-        for tile in tiles:
-            say("Reading tile %s in lane %s" % (tile, lane))
-            tile_bcl = bcl_reader.get_tile(lane, tile)
-            if batch and batch[0][1].num_clusters != tile_bcl.num_clusters:
-                flush()         # one launch covers tiles of one size
-            plane_of = tile_bcl.stage(len(batch), wanted, pool)
-            if args.quiet:
-                tile_bytes = (tile_bcl.num_clusters + 256) * max(1, len(set(wanted)))
-                per_batch = max(1, min(4096, HBM_BUDGET_BYTES // tile_bytes))
-            say("Got %i sequences from %i contiguous cycle ranges." % (n_unique * len(cycles), len(cycles)))
-            batch.append((tile, tile_bcl))
-            if len(batch) >= per_batch:
-                flush()
-        flush()
         output_writer(lane, len(targets), lane_dupl, verbose=not args.summary_only)
 
 

@@ -17,7 +17,6 @@ Integer sums make the result independent of the rank count.
 """
 import os
 import sys
-from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -124,30 +123,28 @@ def main(argv=None):
     mine = plan(len(lanes), len(tiles), rank, world)
     width = 1 + 5 * args.level
     rows = np.zeros((len(mine), width), dtype=np.int64)
-    budget = count_cli.HBM_BUDGET_BYTES
-    pool = ThreadPoolExecutor(max_workers=min(16, os.cpu_count() or 1))
+    # This rank's tiles, lane after lane: files -> page-locked planes on native threads one batch ahead
+    # of the GPU (staging.py); the planes stay in host memory and the fused kernel pulls the sectors
+    # it needs (wd_tile_map_host).
+    from .staging import Stager, lane_batches
+    stager = Stager(threads=max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world)))),
+                    cbcl_cache=rd._cbcl_cache)
+    names = ["%s/%s" % (lanes[int(o) // len(tiles)], tiles[int(o) % len(tiles)]) for o in mine]
+
+    def open_tile(name):
+        lane, tile = name.split("/")
+        return rd.get_tile(lane, tile)
+
     k = 0
     with torch.cuda.stream(stream):
-        while k < len(mine):
-            n_batch = 0
-            first_n = None
-            plane_of = None
-            while k + n_batch < len(mine):
-                o = int(mine[k + n_batch])
-                lane, tile = lanes[o // len(tiles)], tiles[o % len(tiles)]
-                say("Reading tile %s in lane %s" % (tile, lane))
-                t = rd.get_tile(lane, tile)
-                if first_n is None:
-                    first_n = t.num_clusters
-                elif t.num_clusters != first_n:
-                    break
-                plane_of = t.stage(n_batch, wanted, pool)
-                n_batch += 1
-                if n_batch * (first_n + 256) * max(1, len(set(wanted))) > budget or n_batch >= 4096:
-                    break
-            eng.count_async(0, n_batch, [plane_of[c] for c in wanted], args.edit_distance, args.hamming, mode=0)
-            rows[k:k + n_batch] = eng.count_fetch()[1]
-            k += n_batch
+        for got, staged in lane_batches(stager, open_tile, names, wanted):
+            for name in got:
+                say("Reading tile %s in lane %s" % tuple(reversed(name.split("/"))))
+            plane_of = stager.deliver(eng, staged, first_slot=0, zero_copy=True)
+            eng.count_async(0, len(got), [plane_of[c] for c in wanted], args.edit_distance, args.hamming, mode=0)
+            rows[k:k + len(got)] = eng.count_fetch()[1]
+            k += len(got)
+    stager.close()
     buf = exchange_host(rows, mine, len(lanes), len(tiles), width, dist if world > 1 else None) if world == 1 else None
     if world > 1:
         # the counters of many batches live on the host by now: reduce them through a device tensor

@@ -14,8 +14,6 @@ File layout handled (reference lines in brackets):
 import os
 import re
 import struct
-import zlib
-from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
@@ -27,6 +25,7 @@ QUAL_FLAG = 1
 
 _LUT = np.frombuffer(b"ACGTN", dtype=np.uint8)
 _engine = None
+_stager = None
 
 
 def default_engine():
@@ -37,14 +36,32 @@ def default_engine():
     return _engine
 
 
-def gunzip(data):
-    """All members of a gzip byte string (gzip.open semantics)."""
-    out = []
-    while data:
-        d = zlib.decompressobj(wbits=31)
-        out.append(d.decompress(data))
-        data = d.unused_data.lstrip(b"\0")
-    return out[0] if len(out) == 1 else b"".join(out)
+def default_stager(cbcl_cache=None):
+    """Process-wide staging.Stager (two page-locked blocks, native inflate threads)."""
+    global _stager
+    if _stager is None:
+        from .staging import Stager
+        _stager = Stager()
+    if cbcl_cache is not None:
+        _stager._cbcl_cache = cbcl_cache
+    return _stager
+
+
+def gunzip(data, size_hint=None):
+    """All members of a gzip byte string (gzip.open(...).read() semantics), inflated by
+    the library (wd_gunzip).  ``size_hint`` = expected inflated size, if known."""
+    import ctypes as C
+    lib = _lib.load()
+    data = bytes(data)
+    cap = int(size_hint) if size_hint else max(4 * len(data), 1 << 16)
+    while True:
+        out = np.empty(cap, np.uint8)
+        n = C.c_size_t()
+        rc = lib.wd_gunzip(data, len(data), out.ctypes.data, cap, C.byref(n))
+        if rc != _lib.WD_E_CAPACITY:
+            _lib.check(rc)
+            return out[:n.value].tobytes()
+        cap *= 4
 
 
 def codes_to_strings(codes):
@@ -81,8 +98,14 @@ class CbclFile:
         with open(self.path, "rb") as fh:
             fh.seek(off)
             comp = fh.read(csize)
-        data = zlib.decompressobj(wbits=31).decompress(comp, usize)
-        return np.frombuffer(data, dtype=np.uint8), ncl, self.excluded
+        import ctypes as C
+        out = np.empty(max(usize, 1), np.uint8)
+        n = C.c_size_t()
+        rc = _lib.load().wd_gunzip(comp, len(comp), out.ctypes.data, usize, C.byref(n))
+        if rc != _lib.WD_E_CAPACITY:            # GzipFile.read(usize) stops after usize bytes (:301)
+            _lib.check(rc)
+        data = out[:n.value]
+        return data, ncl, self.excluded
 
 
 class BCLReader(object):
@@ -145,38 +168,19 @@ class Tile(object):
             assert struct.unpack("<III", fh.read(12)) == (0, 3, self.num_clusters)
             return np.frombuffer(fh.read(), dtype=np.uint8)[: self.num_clusters]
 
-    def read_cycle(self, cycle):
-        """Inflated payload of 0-based ``cycle``: ("bcl", bytes) or
-        ("cbcl", nibble bytes, clusters in block, excluded)."""
-        cdir = os.path.join(self.data_dir, "C%i.1" % (cycle + 1))
-        try:
-            with open(os.path.join(cdir, self.bcl_filename), "rb") as fh:
-                raw = gunzip(fh.read())
-        except FileNotFoundError:
-            path = os.path.join(cdir, self.cbcl_filename)
-            cf = self._cbcl_cache.get(path)
-            if cf is None:
-                cf = self._cbcl_cache[path] = CbclFile(path)
-            data, ncl, excl = cf.read_tile(self.tile)
-            return ("cbcl", data, ncl, excl)
-        assert struct.unpack("<I", raw[:4])[0] == self.num_clusters
-        return ("bcl", np.frombuffer(raw, dtype=np.uint8, offset=4))
-
-    def stage(self, slot, cycles, pool=None):
+    def stage(self, slot, cycles, pool=None, zero_copy=False):
         """Load the filter and the planes of ``cycles`` (0-based, any order, may
-        repeat) into tile slot ``slot``; returns {cycle: plane index}."""
+        repeat) into tile slot ``slot``; returns {cycle: plane index}.  Files are read
+        and inflated by the library's native threads (staging.Stager) into page-locked
+        memory; ``zero_copy`` leaves them there for the kernels to read in place (the
+        block is reused by the next stage() call), otherwise they are copied to HBM."""
         eng = self.engine
-        uniq = sorted(set(cycles))
-        eng.tile_begin(slot, self.num_clusters, len(uniq))
-        eng.tile_put_filter(slot, self.read_filter())
-        results = pool.map(self.read_cycle, uniq) if pool is not None else map(self.read_cycle, uniq)
-        plane_of = {}
-        for plane, (cyc, payload) in enumerate(zip(uniq, results)):
-            if payload[0] == "bcl":
-                eng.tile_put_bcl(slot, plane, payload[1])
-            else:
-                eng.tile_put_cbcl(slot, plane, payload[1], payload[2], payload[3])
-            plane_of[cyc] = plane
+        st = default_stager(self._cbcl_cache)
+        batch = st.load([self], cycles, which=0)
+        zero_copy = zero_copy and len(batch.cycles) > 0
+        plane_of = st.deliver(eng, batch, first_slot=slot, zero_copy=zero_copy)
+        if not zero_copy:
+            eng.sync()          # the copies read the block the next call overwrites
         return plane_of
 
     # ---- reference API -------------------------------------------------------------
@@ -190,8 +194,9 @@ class Tile(object):
         if keys[0] < 0:
             raise IndexError("Requested cluster %i is a negative number." % keys[0])
         cycles = list(range(start, end))
-        with ThreadPoolExecutor(max_workers=min(8, max(1, len(cycles)))) as pool:
-            plane_of = self.stage(0, cycles, pool)
+        # Few wells: the gather pulls their sectors across PCIe (~0.3 G requests/s) instead of copying
+        # whole planes (~50 GB/s); the two cost the same when about 1 well in 170 is asked for.
+        plane_of = self.stage(0, cycles, zero_copy=len(keys) * 128 < self.num_clusters)
         codes, pf = self.engine.get_seqs(0, keys, [plane_of[c] for c in cycles])
         seqs = codes_to_strings(codes) if cycles else [""] * len(keys)
         return {k: (s, bool(f)) for k, s, f in zip(keys, seqs, pf)}
