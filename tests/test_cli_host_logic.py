@@ -1,0 +1,153 @@
+"""Host logic of the drop-in CLI on top of the staging pipeline, without a GPU.
+
+count_cli.main is run on every golden case with a stand-in for engine.Engine
+whose kernels are the CPU oracle (test infrastructure only: the product has no
+such path and refuses to run without a GPU, test_host_logic.py).  What is
+checked here is everything between the files and the kernels -- tile walk,
+batching, BCL/CBCL choice, native inflate into (pageable) plane blocks, the
+order of the log lines -- against the stdout and stderr of the unmodified
+reference.  The same cases run on the real kernels in test_gpu_parity.py."""
+import contextlib
+import io
+import os
+
+import numpy as np
+import pytest
+
+from helpers import GOLDEN, load_manifest
+from oracle import c_port as CP
+from well_duplicates_b200 import _lib, count_cli, reader, staging
+
+MAN = load_manifest()
+KIND_NAME = {_lib.PLANE_BCL: "bcl", _lib.PLANE_CBCL: "cbcl", _lib.PLANE_CBCL_EXCL: "cbcl_excl"}
+
+
+class OracleEngine:
+    """engine.Engine's staging / counting surface, computed by oracle/c_port."""
+
+    def __init__(self):
+        self.slots = {}
+        self.calls = []
+
+    # -- targets -----------------------------------------------------------------------------------
+    def load_targets(self, centres, level_offsets, idx, levels):
+        self.centres = np.asarray(centres, np.uint32)
+        self.offs = np.asarray(level_offsets, np.uint32)
+        self.idx = np.asarray(idx, np.uint32)
+        self.levels = levels
+
+    # -- staging: views are kept, bytes are read when the count runs (as the kernels do) -------------
+    def tile_map_host(self, slot, n_clusters, pinned_planes, kinds=None, n_block=None, pinned_filter=None):
+        assert pinned_planes.ndim == 2 and pinned_planes.flags.c_contiguous and pinned_filter is not None
+        self.calls.append("map")
+        self.slots[slot] = dict(n=n_clusters, planes=[pinned_planes[p] for p in range(pinned_planes.shape[0])],
+                                kinds=[int(k) for k in kinds], n_block=[int(b) for b in n_block], filt=pinned_filter)
+
+    def tile_begin(self, slot, n_clusters, n_planes):
+        self.calls.append("begin")
+        self.slots[slot] = dict(n=n_clusters, planes=[None] * n_planes, kinds=[0] * n_planes, n_block=[0] * n_planes, filt=None)
+
+    def tile_put_filter(self, slot, filt):
+        assert filt.size == self.slots[slot]["n"]
+        self.slots[slot]["filt"] = filt
+
+    def tile_put_bcl(self, slot, plane, data):
+        s = self.slots[slot]
+        assert data.size == s["n"]
+        s["planes"][plane], s["kinds"][plane], s["n_block"][plane] = data, _lib.PLANE_BCL, data.size
+
+    def tile_put_cbcl(self, slot, plane, nibbles, n_block, excluded):
+        s = self.slots[slot]
+        assert nibbles.size * 2 >= n_block
+        s["planes"][plane], s["n_block"][plane] = nibbles, n_block
+        s["kinds"][plane] = _lib.PLANE_CBCL_EXCL if excluded else _lib.PLANE_CBCL
+
+    def sync(self):
+        pass
+
+    def _tile(self, slot, order):
+        s = self.slots[slot]
+        planes, kinds = [], []
+        for p in order:
+            k = s["kinds"][p]
+            used = s["n_block"][p] if k == _lib.PLANE_BCL else (s["n_block"][p] + 1) // 2
+            planes.append(np.array(s["planes"][p][:used]))
+            kinds.append(KIND_NAME[k])
+        return planes, kinds, np.array(s["filt"][:s["n"]])
+
+    # -- kernels --------------------------------------------------------------------------------------
+    def count(self, first_slot, n_tiles, plane_order, edit_distance=2, hamming=False, mode=0, per_target=True):
+        pts, cnts, self.pairs = [], [], []
+        for k in range(n_tiles):
+            planes, kinds, filt = self._tile(first_slot + k, plane_order)
+            pt, cnt = CP.count_tile(planes, kinds, filt, self.centres, self.offs, self.idx, self.levels, edit_distance, hamming)
+            pts.append(pt)
+            cnts.append(cnt)
+            if mode == 1:
+                wells = np.unique(np.concatenate([self.centres, self.idx]))
+                codes, _ = CP.get_codes(planes, kinds, filt, wells.astype(np.int64))
+                row = {int(w): codes[i] for i, w in enumerate(wells)}
+                for t, c in enumerate(self.centres):
+                    if not pt[t, 0]:
+                        continue
+                    for lev in range(self.levels):
+                        lo, hi = self.offs[t * self.levels + lev], self.offs[t * self.levels + lev + 1]
+                        for w in self.idx[lo:hi]:
+                            a, b = row[int(c)], row[int(w)]
+                            d = int((a != b).sum()) if hamming else CP.levenshtein(a, b)
+                            if d <= edit_distance:
+                                self.pairs.append((k, t, int(w), d))
+        return np.array(pts), np.array(cnts)
+
+    def dup_pairs(self):
+        return np.array(self.pairs, np.int32).reshape(-1, 4)
+
+    def get_seqs(self, slot, indices, plane_order):
+        planes, kinds, filt = self._tile(slot, plane_order)
+        return CP.get_codes(planes, kinds, filt, np.asarray(indices, np.int64))
+
+
+@pytest.fixture()
+def oracle_engine(monkeypatch):
+    eng = OracleEngine()
+    st = staging.Stager(pinned=False, threads=3)
+    monkeypatch.setattr(reader, "_engine", eng)
+    monkeypatch.setattr(reader, "_stager", st)
+    yield eng
+    st.close()
+
+
+@pytest.mark.parametrize("case", MAN["count"], ids=lambda c: c["name"])
+def test_count_cli_host_side_matches_reference(case, oracle_engine):
+    with open(os.path.join(GOLDEN, "count", case["name"] + ".stdout")) as fh:
+        want_out = fh.read()
+    with open(os.path.join(GOLDEN, "count", case["name"] + ".stderr")) as fh:
+        want_err = fh.read()
+    argv = ["-f", os.path.join(GOLDEN, case["targets"]), "-r", os.path.join(GOLDEN, case["run"])] + case["args"]
+    out, err = io.StringIO(), io.StringIO()
+    with contextlib.redirect_stdout(out), contextlib.redirect_stderr(err):
+        if case["returncode"] != 0:
+            with pytest.raises(ZeroDivisionError):
+                count_cli.main(argv)
+        else:
+            count_cli.main(argv)
+    assert out.getvalue() == want_out
+    if case["returncode"] == 0:
+        assert err.getvalue() == want_err
+    quiet = "-q" in case["args"] or "--quiet" in case["args"]
+    # -q: planes stay where the inflate put them; otherwise they are copied for the two-pass kernels
+    assert set(oracle_engine.calls) == ({"map"} if quiet else {"begin"})
+
+
+def test_quiet_and_logged_runs_print_the_same_report(oracle_engine):
+    """Batched zero-copy walk (-q) and tile-by-tile walk give one report."""
+    case = [c for c in MAN["count"] if c["name"] == "two_lanes"][0] if any(c["name"] == "two_lanes" for c in MAN["count"]) else MAN["count"][0]
+    base = ["-f", os.path.join(GOLDEN, case["targets"]), "-r", os.path.join(GOLDEN, case["run"])] + [a for a in case["args"] if a not in ("-q", "--quiet")]
+    outs = []
+    for extra in ([], ["-q"]):
+        out, err = io.StringIO(), io.StringIO()
+        with contextlib.redirect_stdout(out), contextlib.redirect_stderr(err):
+            count_cli.main(base + extra)
+        outs.append(out.getvalue())
+        assert (err.getvalue() == "") == bool(extra)
+    assert outs[0] == outs[1] and outs[0]
