@@ -178,8 +178,11 @@ uint32_t crc32_update(uint32_t crc, const uint8_t *p, size_t n) {
 //   bits 0..5    bits to drop from the bit buffer (code length [+ extra bits];
 //                for a pointer: the first-level width)
 //   bits 6..7    kind
-//   bits 8..11   code length (base + extra entries) / second-level width (pointer)
-//   bits 16..31  literal byte / base value / index of the second-level table
+//   bits 8..11   code length (base + extra entries; first code of a literal entry) /
+//                second-level width (pointer)
+//   bit  12      literal entries of the first level: a second literal follows in bits 24..31
+//                (two short codes decoded by one lookup; bits 0..5 then cover both codes)
+//   bits 16..31  literal byte(s) / base value / index of the second-level table
 enum : uint32_t { K_LITERAL = 0u << 6, K_BASE = 1u << 6, K_POINTER = 2u << 6, K_SPECIAL = 3u << 6, K_MASK = 3u << 6 };
 constexpr uint32_t ENTRY_INVALID = K_SPECIAL | (1u << 16) | 1u;   // drops one bit, never reached twice
 constexpr uint32_t ENTRY_EOB_PAYLOAD = 0;
@@ -209,7 +212,7 @@ inline uint32_t symbol_entry(TableKind kind, int sym, int len) {
     case T_PRECODE:
         return K_LITERAL | ((uint32_t)sym << 16) | (uint32_t)len;
     case T_LITLEN:
-        if (sym < 256) return K_LITERAL | ((uint32_t)sym << 16) | (uint32_t)len;
+        if (sym < 256) return K_LITERAL | ((uint32_t)sym << 16) | ((uint32_t)len << 8) | (uint32_t)len;
         if (sym == 256) return K_SPECIAL | (ENTRY_EOB_PAYLOAD << 16) | (uint32_t)len;
         if (sym > 285) return K_SPECIAL | (1u << 16) | (uint32_t)len;       // 286, 287: never valid in data
         return K_BASE | ((uint32_t)LEN_BASE[sym - 257] << 16) | ((uint32_t)len << 8) | (uint32_t)(len + LEN_EXTRA[sym - 257]);
@@ -292,6 +295,23 @@ bool build_table(TableKind kind, const uint8_t *lens, int n_syms, int first_bits
             for (int i = sym_code[s] >> first_bits; i < (1 << bits); i += 1 << rest) table[base + i] = e;
         }
     }
+    if (kind == T_LITLEN) {
+        // Pairs of literals: where the code of a literal leaves room in the index for the whole code of
+        // the literal after it, the entry delivers both.  Ascending order: entry i >> len (the bits after
+        // the first code, zero-extended) has been visited already or is a plain single -- either way its
+        // first literal and the length of its first code are what is needed.
+        for (int i = 0; i < first_size; ++i) {
+            const uint32_t e1 = table[i];
+            if ((e1 & K_MASK) != K_LITERAL) continue;
+            const int l1 = (int)(e1 & 63);
+            if (l1 >= first_bits) continue;
+            const uint32_t e2 = table[i >> l1];
+            if ((e2 & K_MASK) != K_LITERAL) continue;
+            const int l2 = (int)((e2 >> 8) & 15);
+            if (l1 + l2 > first_bits) continue;
+            table[i] = K_LITERAL | (1u << 12) | (((e2 >> 16) & 0xffu) << 24) | (e1 & 0x00ff0000u) | ((uint32_t)l1 << 8) | (uint32_t)(l1 + l2);
+        }
+    }
     return true;
 }
 
@@ -313,6 +333,8 @@ struct Inflater {
     // what was consumed / produced (also on error, as far as it got).
     int inflate_raw(const uint8_t *in, size_t in_len, uint8_t *out, size_t out_cap, size_t *in_used, size_t *out_len);
 };
+
+inline void store16(uint8_t *p, uint16_t v) { memcpy(p, &v, 2); }
 
 inline uint64_t load64(const uint8_t *p) {
     uint64_t v;
@@ -497,17 +519,21 @@ int Inflater::inflate_raw(const uint8_t *const in, const size_t in_len, uint8_t 
                 uint32_t e = LOOKUP_LITLEN();
                 do {
                     if ((e & K_MASK) == K_LITERAL) {
-                        // up to three first-level literals (<= 33 bits) leave >= 23 valid bits for the lookup after them
+                        // up to three first-level entries (one or two literals each, <= 36 bits) leave >= 20 valid
+                        // bits for the lookup after them
                         DROP(e & 63);
-                        *op++ = (uint8_t)(e >> 16);
+                        store16(op, (uint16_t)(e >> 16));
+                        op += 1 + ((e >> 12) & 1);
                         e = LOOKUP_LITLEN();
                         if ((e & K_MASK) == K_LITERAL) {
                             DROP(e & 63);
-                            *op++ = (uint8_t)(e >> 16);
+                            store16(op, (uint16_t)(e >> 16));
+                            op += 1 + ((e >> 12) & 1);
                             e = LOOKUP_LITLEN();
                             if ((e & K_MASK) == K_LITERAL) {
                                 DROP(e & 63);
-                                *op++ = (uint8_t)(e >> 16);
+                                store16(op, (uint16_t)(e >> 16));
+                                op += 1 + ((e >> 12) & 1);
                                 e = LOOKUP_LITLEN();
                             }
                         }
@@ -583,7 +609,7 @@ int Inflater::inflate_raw(const uint8_t *const in, const size_t in_len, uint8_t 
                 e = lt[(e >> 16) + BITS((e >> 8) & 15)];
             }
             if ((e & K_MASK) == K_LITERAL) {
-                DROP(e & 63);
+                DROP((e >> 8) & 15);         // one literal at a time here: the first code of the entry
                 if (bitcnt < 0) { rc = fail(INF_TRUNCATED, "stream ends inside a block"); goto done; }
                 if (op == out_end) { rc = fail(INF_OUT_FULL, "output buffer full"); goto done; }
                 *op++ = (uint8_t)(e >> 16);
