@@ -6,8 +6,10 @@
 // and cycle in bcl_direct_reader.py:207-208, :300-301, ~0.1 GB/s per core with
 // zlib on base-call bytes).  This file replaces that step with
 //   * an inflate written for this data: 64-bit bit buffer refilled branch-free,
-//     an 11-bit first-level literal/length table, runs of literals decoded
-//     without touching the refill, matches copied in 16-byte pieces;
+//     a 10-bit first-level literal/length table whose entries deliver two literals,
+//     or a whole short match (length + distance code), per lookup where the codes
+//     fit the index; the next entry is looked up before the match copy; matches
+//     are copied in 16-byte pieces;
 //   * CRC-32 by carry-less multiplication (PCLMULQDQ folding), table fallback;
 //   * a job list executed by a pool of native threads (file read + inflate +
 //     check, no Python in the loop), writing each member where the caller says.
@@ -175,27 +177,34 @@ uint32_t crc32_update(uint32_t crc, const uint8_t *p, size_t n) {
 // DEFLATE (RFC 1951)
 // ---------------------------------------------------------------------------------------------
 // Decode-table entry (32 bits):
-//   bits 0..5    bits to drop from the bit buffer (code length [+ extra bits];
+//   bits 0..4    bits to drop from the bit buffer (code length [+ extra bits]; both codes of a
+//                literal pair; length code + distance code + distance extra bits of a fused match;
 //                for a pointer: the first-level width)
-//   bits 6..7    kind
-//   bits 8..11   code length (base + extra entries; first code of a literal entry) /
-//                second-level width (pointer)
+//   bits 5..7    kind
+//   bits 8..11   where the extra bits start = code length (base + extra entries; both codes of a
+//                fused match) / code length of the first literal / second-level width (pointer)
 //   bit  12      literal entries of the first level: a second literal follows in bits 24..31
-//                (two short codes decoded by one lookup; bits 0..5 then cover both codes)
+//                (two short codes decoded by one lookup)
+//   bits 12..14  fused match: length - 3
 //   bits 16..31  literal byte(s) / base value / index of the second-level table
-enum : uint32_t { K_LITERAL = 0u << 6, K_BASE = 1u << 6, K_POINTER = 2u << 6, K_SPECIAL = 3u << 6, K_MASK = 3u << 6 };
+enum : uint32_t {
+    K_LITERAL = 0u << 5, K_BASE = 1u << 5, K_POINTER = 2u << 5, K_SPECIAL = 3u << 5,
+    K_MATCH = 4u << 5,          // length code without extra bits + whole distance code in one first-level entry
+    K_MASK = 7u << 5
+};
+#define NB(e) ((e) & 31u)
 constexpr uint32_t ENTRY_INVALID = K_SPECIAL | (1u << 16) | 1u;   // drops one bit, never reached twice
 constexpr uint32_t ENTRY_EOB_PAYLOAD = 0;
 
-constexpr int LITLEN_BITS = 11;
+constexpr int LITLEN_BITS = 10;      // 10 vs 11 vs 12 measured on base-call planes: table build per block outweighs the extra pairs
 constexpr int DIST_BITS = 8;
 constexpr int PRE_BITS = 7;
 constexpr int LITLEN_SYMS = 288;
 constexpr int DIST_SYMS = 32;
 // first level + second-level tables: every long code owns at most one second-level table of
 // 2^(15 - first level) entries (a loose bound; build_table checks it anyway)
-constexpr int LITLEN_TABLE = (1 << LITLEN_BITS) + 288 * 16;
-constexpr int DIST_TABLE = (1 << DIST_BITS) + 32 * 128;
+constexpr int LITLEN_TABLE = (1 << LITLEN_BITS) + 288 * (1 << (15 - LITLEN_BITS));
+constexpr int DIST_TABLE = (1 << DIST_BITS) + 32 * (1 << (15 - DIST_BITS));
 
 const uint16_t LEN_BASE[29] = {3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258};
 const uint8_t LEN_EXTRA[29] = {0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0};
@@ -222,13 +231,13 @@ inline uint32_t symbol_entry(TableKind kind, int sym, int len) {
     }
 }
 
-inline uint32_t bit_reverse(uint32_t code, int len) {
-    uint32_t r = 0;
-    for (int i = 0; i < len; ++i) {
-        r = (r << 1) | (code & 1);
-        code >>= 1;
-    }
-    return r;
+inline uint32_t bit_reverse(uint32_t code, int len) {      // len <= 15
+    uint32_t v = code;
+    v = ((v & 0x5555u) << 1) | ((v >> 1) & 0x5555u);
+    v = ((v & 0x3333u) << 2) | ((v >> 2) & 0x3333u);
+    v = ((v & 0x0f0fu) << 4) | ((v >> 4) & 0x0f0fu);
+    v = ((v & 0x00ffu) << 8) | ((v >> 8) & 0x00ffu);
+    return v >> (16 - len);
 }
 
 // Canonical Huffman code -> two-level lookup table indexed by the next bits of
@@ -240,14 +249,18 @@ bool build_table(TableKind kind, const uint8_t *lens, int n_syms, int first_bits
     int max_len = 15;
     while (max_len > 0 && count[max_len] == 0) --max_len;
     const int first_size = 1 << first_bits;
-    for (int i = 0; i < first_size; ++i) table[i] = ENTRY_INVALID;
-    if (max_len == 0) return true;            // no codes at all: any use of the table is an error
+    if (max_len == 0) {                       // no codes at all: any use of the table is an error
+        for (int i = 0; i < first_size; ++i) table[i] = ENTRY_INVALID;
+        return true;
+    }
     int left = 1;
     for (int l = 1; l <= 15; ++l) {
         left = (left << 1) - count[l];
         if (left < 0) return false;           // over-subscribed
     }
     if (left > 0 && (kind == T_PRECODE || max_len != 1)) return false;   // incomplete (inftrees.c rule)
+    if (left > 0)                             // a complete code covers every first-level entry below
+        for (int i = 0; i < first_size; ++i) table[i] = ENTRY_INVALID;
     uint32_t next_code[16];
     uint32_t code = 0;
     for (int l = 1; l <= 15; ++l) {
@@ -295,24 +308,48 @@ bool build_table(TableKind kind, const uint8_t *lens, int n_syms, int first_bits
             for (int i = sym_code[s] >> first_bits; i < (1 << bits); i += 1 << rest) table[base + i] = e;
         }
     }
-    if (kind == T_LITLEN) {
-        // Pairs of literals: where the code of a literal leaves room in the index for the whole code of
-        // the literal after it, the entry delivers both.  Ascending order: entry i >> len (the bits after
-        // the first code, zero-extended) has been visited already or is a plain single -- either way its
-        // first literal and the length of its first code are what is needed.
-        for (int i = 0; i < first_size; ++i) {
-            const uint32_t e1 = table[i];
-            if ((e1 & K_MASK) != K_LITERAL) continue;
-            const int l1 = (int)(e1 & 63);
-            if (l1 >= first_bits) continue;
-            const uint32_t e2 = table[i >> l1];
+    return true;
+}
+
+// Second pass over the first level of a literal/length table, after the distance table of the block exists.
+//
+// Pairs of literals: where the code of a literal leaves room in the index for the whole code of the
+// literal after it, the entry delivers both (literal decode is a dependent load -> shift -> mask
+// chain; two per lookup nearly halve it).  Ascending order: entry i >> len (the bits after the
+// first code, zero-extended) has been visited already or is a plain single -- either way its first
+// literal and the length of its first code are what is needed.
+//
+// Fused matches: base-call planes deflate into short chance matches (3..5 bytes) at distances of
+// thousands: a short length code followed by a short distance code.  Where a length code without
+// extra bits leaves room in the index for the whole distance code, one entry delivers the match --
+// length, distance base and where the distance's extra bits are: one dependent table load per match
+// instead of two.
+void combine_entries(uint32_t *litlen, const uint32_t *dist) {
+    const int first_size = 1 << LITLEN_BITS;
+    for (int i = 0; i < first_size; ++i) {
+        const uint32_t e1 = litlen[i];
+        const uint32_t k1 = e1 & K_MASK;
+        if (k1 == K_LITERAL) {
+            const int l1 = (int)NB(e1);
+            if (l1 >= LITLEN_BITS) continue;
+            const uint32_t e2 = litlen[i >> l1];
             if ((e2 & K_MASK) != K_LITERAL) continue;
             const int l2 = (int)((e2 >> 8) & 15);
-            if (l1 + l2 > first_bits) continue;
-            table[i] = K_LITERAL | (1u << 12) | (((e2 >> 16) & 0xffu) << 24) | (e1 & 0x00ff0000u) | ((uint32_t)l1 << 8) | (uint32_t)(l1 + l2);
+            if (l1 + l2 > LITLEN_BITS) continue;
+            litlen[i] = K_LITERAL | (1u << 12) | (((e2 >> 16) & 0xffu) << 24) | (e1 & 0x00ff0000u) | ((uint32_t)l1 << 8) | (uint32_t)(l1 + l2);
+        } else if (k1 == K_BASE) {
+            const int l1 = (int)((e1 >> 8) & 15);
+            if ((int)NB(e1) != l1) continue;                          // the length has extra bits
+            const uint32_t length = e1 >> 16;
+            if (length > 10 || l1 >= LITLEN_BITS) continue;
+            const uint32_t e2 = dist[(i >> l1) & ((1 << DIST_BITS) - 1)];
+            if ((e2 & K_MASK) != K_BASE) continue;
+            const int l2 = (int)((e2 >> 8) & 15);
+            if (l1 + l2 > LITLEN_BITS) continue;                      // the index does not hold the whole distance code
+            const int extra = (int)NB(e2) - l2;
+            litlen[i] = K_MATCH | (e2 & 0xffff0000u) | ((length - 3) << 12) | ((uint32_t)(l1 + l2) << 8) | (uint32_t)(l1 + l2 + extra);
         }
     }
-    return true;
 }
 
 struct Inflater {
@@ -414,6 +451,7 @@ int Inflater::inflate_raw(const uint8_t *const in, const size_t in_len, uint8_t 
                 build_table(T_LITLEN, lens, 288, LITLEN_BITS, fixed_litlen, LITLEN_TABLE);
                 for (int s = 0; s < 32; ++s) lens[s] = 5;
                 build_table(T_DIST, lens, 32, DIST_BITS, fixed_dist, DIST_TABLE);
+                combine_entries(fixed_litlen, fixed_dist);
                 fixed_ready = true;
             }
             lt = fixed_litlen;
@@ -445,7 +483,7 @@ int Inflater::inflate_raw(const uint8_t *const in, const size_t in_len, uint8_t 
             while (have < total) {
                 REFILL_SAFE();
                 const uint32_t e = pre[BITS(PRE_BITS)];
-                const int nb = (int)(e & 63);
+                const int nb = (int)NB(e);
                 if (nb > bitcnt) { rc = fail(INF_TRUNCATED, "stream ends inside a block header"); goto done; }
                 if ((e & K_MASK) != K_LITERAL) { rc = fail(INF_BAD_DATA, "invalid code lengths set"); goto done; }
                 const int sym = (int)(e >> 16);
@@ -488,6 +526,7 @@ int Inflater::inflate_raw(const uint8_t *const in, const size_t in_len, uint8_t 
                 rc = fail(INF_BAD_DATA, "invalid distances set");
                 goto done;
             }
+            combine_entries(litlen, dist);
             lt = litlen;
             dt = dist;
         } else {
@@ -519,19 +558,19 @@ int Inflater::inflate_raw(const uint8_t *const in, const size_t in_len, uint8_t 
                 uint32_t e = LOOKUP_LITLEN();
                 do {
                     if ((e & K_MASK) == K_LITERAL) {
-                        // up to three first-level entries (one or two literals each, <= 36 bits) leave >= 20 valid
-                        // bits for the lookup after them
-                        DROP(e & 63);
+                        // up to three first-level entries (one or two literals each, <= 3 x LITLEN_BITS bits) leave
+                        // more than the 15 valid bits the lookup after them may need
+                        DROP(NB(e));
                         store16(op, (uint16_t)(e >> 16));
                         op += 1 + ((e >> 12) & 1);
                         e = LOOKUP_LITLEN();
                         if ((e & K_MASK) == K_LITERAL) {
-                            DROP(e & 63);
+                            DROP(NB(e));
                             store16(op, (uint16_t)(e >> 16));
                             op += 1 + ((e >> 12) & 1);
                             e = LOOKUP_LITLEN();
                             if ((e & K_MASK) == K_LITERAL) {
-                                DROP(e & 63);
+                                DROP(NB(e));
                                 store16(op, (uint16_t)(e >> 16));
                                 op += 1 + ((e >> 12) & 1);
                                 e = LOOKUP_LITLEN();
@@ -540,34 +579,42 @@ int Inflater::inflate_raw(const uint8_t *const in, const size_t in_len, uint8_t 
                         REFILL_FAST();
                         continue;
                     }
-                    if ((e & K_MASK) == K_POINTER) {
-                        DROP(LITLEN_BITS);
-                        e = lt[(e >> 16) + BITS((e >> 8) & 15)];
-                        if ((e & K_MASK) == K_LITERAL) {
-                            DROP(e & 63);
-                            *op++ = (uint8_t)(e >> 16);
-                            e = LOOKUP_LITLEN();
-                            REFILL_FAST();
-                            continue;
+                    uint32_t length, distance;
+                    if ((e & K_MASK) == K_MATCH) {
+                        // length and distance code from one entry; only the distance's extra bits are left to read
+                        length = 3 + ((e >> 12) & 7);
+                        distance = (e >> 16) + (((uint32_t)bitbuf >> ((e >> 8) & 15)) & ((1u << (NB(e) - ((e >> 8) & 15))) - 1u));
+                        DROP(NB(e));
+                    } else {
+                        if ((e & K_MASK) == K_POINTER) {
+                            DROP(LITLEN_BITS);
+                            e = lt[(e >> 16) + BITS((e >> 8) & 15)];
+                            if ((e & K_MASK) == K_LITERAL) {
+                                DROP(NB(e));
+                                *op++ = (uint8_t)(e >> 16);
+                                e = LOOKUP_LITLEN();
+                                REFILL_FAST();
+                                continue;
+                            }
                         }
+                        if ((e & K_MASK) == K_SPECIAL) {
+                            if ((e >> 16) != ENTRY_EOB_PAYLOAD) { rc = fail(INF_BAD_DATA, "invalid literal/length code"); goto done; }
+                            DROP(NB(e));
+                            block_done = true;
+                            break;
+                        }
+                        // length (<= 20 bits with the pointer step), distance (<= 28 bits): 48 of the 56
+                        length = (e >> 16) + (((uint32_t)bitbuf >> ((e >> 8) & 15)) & ((1u << (NB(e) - ((e >> 8) & 15))) - 1u));
+                        DROP(NB(e));
+                        e = dt[bitbuf & ((1u << DIST_BITS) - 1u)];
+                        if ((e & K_MASK) == K_POINTER) {
+                            DROP(DIST_BITS);
+                            e = dt[(e >> 16) + BITS((e >> 8) & 15)];
+                        }
+                        if ((e & K_MASK) != K_BASE) { rc = fail(INF_BAD_DATA, "invalid distance code"); goto done; }
+                        distance = (e >> 16) + (((uint32_t)bitbuf >> ((e >> 8) & 15)) & ((1u << (NB(e) - ((e >> 8) & 15))) - 1u));
+                        DROP(NB(e));
                     }
-                    if ((e & K_MASK) == K_SPECIAL) {
-                        if ((e >> 16) != ENTRY_EOB_PAYLOAD) { rc = fail(INF_BAD_DATA, "invalid literal/length code"); goto done; }
-                        DROP(e & 63);
-                        block_done = true;
-                        break;
-                    }
-                    // length (<= 20 bits with the pointer step), distance (<= 28 bits): 48 of the 56
-                    const uint32_t length = (e >> 16) + (((uint32_t)bitbuf >> ((e >> 8) & 15)) & ((1u << ((e & 63) - ((e >> 8) & 15))) - 1u));
-                    DROP(e & 63);
-                    e = dt[bitbuf & ((1u << DIST_BITS) - 1u)];
-                    if ((e & K_MASK) == K_POINTER) {
-                        DROP(DIST_BITS);
-                        e = dt[(e >> 16) + BITS((e >> 8) & 15)];
-                    }
-                    if ((e & K_MASK) != K_BASE) { rc = fail(INF_BAD_DATA, "invalid distance code"); goto done; }
-                    const uint32_t distance = (e >> 16) + (((uint32_t)bitbuf >> ((e >> 8) & 15)) & ((1u << ((e & 63) - ((e >> 8) & 15))) - 1u));
-                    DROP(e & 63);
                     if (distance > (size_t)(op - out)) { rc = fail(INF_BAD_DATA, "invalid distance too far back"); goto done; }
                     REFILL_FAST();
                     e = LOOKUP_LITLEN();
@@ -616,28 +663,36 @@ int Inflater::inflate_raw(const uint8_t *const in, const size_t in_len, uint8_t 
                 continue;
             }
             if ((e & K_MASK) == K_SPECIAL) {
-                if ((int)(e & 63) > bitcnt && ip == in_end) { rc = fail(INF_TRUNCATED, "stream ends inside a block"); goto done; }
+                if ((int)NB(e) > bitcnt && ip == in_end) { rc = fail(INF_TRUNCATED, "stream ends inside a block"); goto done; }
                 if ((e >> 16) != ENTRY_EOB_PAYLOAD) { rc = fail(INF_BAD_DATA, "invalid literal/length code"); goto done; }
-                DROP(e & 63);
+                DROP(NB(e));
                 break;
             }
-            uint32_t length = (e >> 16) + (((uint32_t)bitbuf >> ((e >> 8) & 15)) & ((1u << ((e & 63) - ((e >> 8) & 15))) - 1u));
-            DROP(e & 63);
-            if (bitcnt < 0) { rc = fail(INF_TRUNCATED, "stream ends inside a block"); goto done; }
-            REFILL_SAFE();
-            e = dt[BITS(DIST_BITS)];
-            if ((e & K_MASK) == K_POINTER) {
-                DROP(DIST_BITS);
-                e = dt[(e >> 16) + BITS((e >> 8) & 15)];
+            uint32_t length, distance;
+            if ((e & K_MASK) == K_MATCH) {
+                length = 3 + ((e >> 12) & 7);
+                distance = (e >> 16) + (((uint32_t)bitbuf >> ((e >> 8) & 15)) & ((1u << (NB(e) - ((e >> 8) & 15))) - 1u));
+                DROP(NB(e));
+                if (bitcnt < 0) { rc = fail(INF_TRUNCATED, "stream ends inside a block"); goto done; }
+            } else {
+                length = (e >> 16) + (((uint32_t)bitbuf >> ((e >> 8) & 15)) & ((1u << (NB(e) - ((e >> 8) & 15))) - 1u));
+                DROP(NB(e));
+                if (bitcnt < 0) { rc = fail(INF_TRUNCATED, "stream ends inside a block"); goto done; }
+                REFILL_SAFE();
+                e = dt[BITS(DIST_BITS)];
+                if ((e & K_MASK) == K_POINTER) {
+                    DROP(DIST_BITS);
+                    e = dt[(e >> 16) + BITS((e >> 8) & 15)];
+                }
+                if ((e & K_MASK) != K_BASE) {
+                    if ((int)NB(e) > bitcnt && ip == in_end) { rc = fail(INF_TRUNCATED, "stream ends inside a block"); goto done; }
+                    rc = fail(INF_BAD_DATA, "invalid distance code");
+                    goto done;
+                }
+                distance = (e >> 16) + (((uint32_t)bitbuf >> ((e >> 8) & 15)) & ((1u << (NB(e) - ((e >> 8) & 15))) - 1u));
+                DROP(NB(e));
+                if (bitcnt < 0) { rc = fail(INF_TRUNCATED, "stream ends inside a block"); goto done; }
             }
-            if ((e & K_MASK) != K_BASE) {
-                if ((int)(e & 63) > bitcnt && ip == in_end) { rc = fail(INF_TRUNCATED, "stream ends inside a block"); goto done; }
-                rc = fail(INF_BAD_DATA, "invalid distance code");
-                goto done;
-            }
-            const uint32_t distance = (e >> 16) + (((uint32_t)bitbuf >> ((e >> 8) & 15)) & ((1u << ((e & 63) - ((e >> 8) & 15))) - 1u));
-            DROP(e & 63);
-            if (bitcnt < 0) { rc = fail(INF_TRUNCATED, "stream ends inside a block"); goto done; }
             if (distance > (size_t)(op - out)) { rc = fail(INF_BAD_DATA, "invalid distance too far back"); goto done; }
             if (length > (size_t)(out_end - op)) {
                 // fill what fits, like zlib, then report
