@@ -183,9 +183,8 @@ uint32_t crc32_update(uint32_t crc, const uint8_t *p, size_t n) {
 //   bits 5..7    kind
 //   bits 8..11   where the extra bits start = code length (base + extra entries; both codes of a
 //                fused match) / code length of the first literal / second-level width (pointer)
-//   bit  12      literal entries of the first level: a second literal follows in bits 24..31
-//                (two short codes decoded by one lookup)
-//   bits 12..14  fused match: length - 3
+//   bits 12..15  bytes the entry produces: 1 literal, 2 literals (the second one in bits 24..31: two
+//                short codes decoded by one lookup), length 3..10 of a fused match
 //   bits 16..31  literal byte(s) / base value / index of the second-level table
 enum : uint32_t {
     K_LITERAL = 0u << 5, K_BASE = 1u << 5, K_POINTER = 2u << 5, K_SPECIAL = 3u << 5,
@@ -221,7 +220,7 @@ inline uint32_t symbol_entry(TableKind kind, int sym, int len) {
     case T_PRECODE:
         return K_LITERAL | ((uint32_t)sym << 16) | (uint32_t)len;
     case T_LITLEN:
-        if (sym < 256) return K_LITERAL | ((uint32_t)sym << 16) | ((uint32_t)len << 8) | (uint32_t)len;
+        if (sym < 256) return K_LITERAL | ((uint32_t)sym << 16) | (1u << 12) | ((uint32_t)len << 8) | (uint32_t)len;
         if (sym == 256) return K_SPECIAL | (ENTRY_EOB_PAYLOAD << 16) | (uint32_t)len;
         if (sym > 285) return K_SPECIAL | (1u << 16) | (uint32_t)len;       // 286, 287: never valid in data
         return K_BASE | ((uint32_t)LEN_BASE[sym - 257] << 16) | ((uint32_t)len << 8) | (uint32_t)(len + LEN_EXTRA[sym - 257]);
@@ -324,8 +323,9 @@ bool build_table(TableKind kind, const uint8_t *lens, int n_syms, int first_bits
 // extra bits leaves room in the index for the whole distance code, one entry delivers the match --
 // length, distance base and where the distance's extra bits are: one dependent table load per match
 // instead of two.
-void combine_entries(uint32_t *litlen, const uint32_t *dist) {
+int combine_entries(uint32_t *litlen, const uint32_t *dist) {
     const int first_size = 1 << LITLEN_BITS;
+    int fused = 0;
     for (int i = 0; i < first_size; ++i) {
         const uint32_t e1 = litlen[i];
         const uint32_t k1 = e1 & K_MASK;
@@ -336,7 +336,7 @@ void combine_entries(uint32_t *litlen, const uint32_t *dist) {
             if ((e2 & K_MASK) != K_LITERAL) continue;
             const int l2 = (int)((e2 >> 8) & 15);
             if (l1 + l2 > LITLEN_BITS) continue;
-            litlen[i] = K_LITERAL | (1u << 12) | (((e2 >> 16) & 0xffu) << 24) | (e1 & 0x00ff0000u) | ((uint32_t)l1 << 8) | (uint32_t)(l1 + l2);
+            litlen[i] = K_LITERAL | (2u << 12) | (((e2 >> 16) & 0xffu) << 24) | (e1 & 0x00ff0000u) | ((uint32_t)l1 << 8) | (uint32_t)(l1 + l2);
         } else if (k1 == K_BASE) {
             const int l1 = (int)((e1 >> 8) & 15);
             if ((int)NB(e1) != l1) continue;                          // the length has extra bits
@@ -347,9 +347,11 @@ void combine_entries(uint32_t *litlen, const uint32_t *dist) {
             const int l2 = (int)((e2 >> 8) & 15);
             if (l1 + l2 > LITLEN_BITS) continue;                      // the index does not hold the whole distance code
             const int extra = (int)NB(e2) - l2;
-            litlen[i] = K_MATCH | (e2 & 0xffff0000u) | ((length - 3) << 12) | ((uint32_t)(l1 + l2) << 8) | (uint32_t)(l1 + l2 + extra);
+            litlen[i] = K_MATCH | (e2 & 0xffff0000u) | (length << 12) | ((uint32_t)(l1 + l2) << 8) | (uint32_t)(l1 + l2 + extra);
+            ++fused;
         }
     }
+    return fused;
 }
 
 struct Inflater {
@@ -358,7 +360,7 @@ struct Inflater {
     uint32_t fixed_litlen[LITLEN_TABLE];
     uint32_t fixed_dist[DIST_TABLE];
     uint32_t pre[1 << PRE_BITS];
-    bool fixed_ready = false;
+    bool fixed_ready = false, fixed_fused = false;
     const char *why = "";
 
     int fail(int rc, const char *msg) {
@@ -409,6 +411,7 @@ int Inflater::inflate_raw(const uint8_t *const in, const size_t in_len, uint8_t 
         const uint32_t type = (BITS(3) >> 1);
         DROP(3);
         const uint32_t *lt, *dt;
+        bool uniform = false;        // the block's table holds fused matches: take literals and matches through one branch-free step
         if (type == 0) {
             // stored: back to a byte boundary, hand unread whole bytes back to the input
             DROP(bitcnt & 7);
@@ -451,11 +454,12 @@ int Inflater::inflate_raw(const uint8_t *const in, const size_t in_len, uint8_t 
                 build_table(T_LITLEN, lens, 288, LITLEN_BITS, fixed_litlen, LITLEN_TABLE);
                 for (int s = 0; s < 32; ++s) lens[s] = 5;
                 build_table(T_DIST, lens, 32, DIST_BITS, fixed_dist, DIST_TABLE);
-                combine_entries(fixed_litlen, fixed_dist);
+                fixed_fused = combine_entries(fixed_litlen, fixed_dist) > 0;
                 fixed_ready = true;
             }
             lt = fixed_litlen;
             dt = fixed_dist;
+            uniform = fixed_fused;
         } else if (type == 2) {
             REFILL_SAFE();
             if (bitcnt < 14) { rc = fail(INF_TRUNCATED, "stream ends inside a block header"); goto done; }
@@ -526,7 +530,7 @@ int Inflater::inflate_raw(const uint8_t *const in, const size_t in_len, uint8_t 
                 rc = fail(INF_BAD_DATA, "invalid distances set");
                 goto done;
             }
-            combine_entries(litlen, dist);
+            uniform = combine_entries(litlen, dist) > 0;
             lt = litlen;
             dt = dist;
         } else {
@@ -556,23 +560,58 @@ int Inflater::inflate_raw(const uint8_t *const in, const size_t in_len, uint8_t 
 #define LOOKUP_LITLEN() lt[bitbuf & ((1u << LITLEN_BITS) - 1u)]
                 REFILL_FAST();
                 uint32_t e = LOOKUP_LITLEN();
+// Blocks that mix literals and short matches (every base-call plane): which of the two comes next
+// is a coin toss per symbol, and a mispredicted branch costs more than either.  Literal entries (one
+// or two bytes) and fused match entries have one shape -- bits to drop, bytes produced, 16 payload
+// bits -- so one step serves both without a branch: a 16-byte copy from `op - distance` to `op` for a
+// match, from a scratch block onto itself for a literal, and the literal bytes stored to `op` or to
+// scratch.  Only what is rare branches: a distance below 16 (the 16-byte copy would overlap) or
+// beyond the start of the output.
+#define UNIFORM_STEP()                                                                                              \
+    {                                                                                                               \
+        const uint32_t is_match = (e >> 7) & 1u;                                                                    \
+        const uint32_t pos = (e >> 8) & 15u, nb = NB(e);                                                            \
+        const uint32_t payload = e >> 16;                                                                           \
+        const uint32_t distance = payload + (((uint32_t)bitbuf >> pos) & ((1u << (nb - pos)) - 1u));                \
+        const uint32_t adv = (e >> 12) & 15u;                                                                       \
+        DROP(nb);                                                                                                   \
+        e = LOOKUP_LITLEN();                                                                                        \
+        const uint32_t rare = is_match & ((uint32_t)(distance < 16) | (uint32_t)(distance > (size_t)(op - out)));  \
+        if (__builtin_expect(rare, 0)) {                                                                            \
+            if (distance > (size_t)(op - out)) { rc = fail(INF_BAD_DATA, "invalid distance too far back"); goto done; } \
+            for (uint32_t k = 0; k < adv; ++k) op[k] = op[(ptrdiff_t)k - (ptrdiff_t)distance];                      \
+        } else {                                                                                                    \
+            const uintptr_t m = (uintptr_t)0 - (uintptr_t)is_match;                                                 \
+            const uintptr_t su = (uintptr_t)scratch, ou = (uintptr_t)op;                                            \
+            memcpy((uint8_t *)(su + ((ou - su) & m)), (const uint8_t *)(su + ((ou - distance - su) & m)), 16);      \
+            store16((uint8_t *)(ou + ((su + 16 - ou) & m)), (uint16_t)payload);                                     \
+        }                                                                                                           \
+        op += adv;                                                                                                  \
+    }
+                alignas(16) uint8_t scratch[32] = {0};
                 do {
+                    if (uniform && (e & (3u << 5)) == 0) {          // K_LITERAL or K_MATCH
+                        UNIFORM_STEP();                             // <= 23 bits each: two fit one refill
+                        if ((e & (3u << 5)) == 0) UNIFORM_STEP();
+                        REFILL_FAST();
+                        continue;
+                    }
                     if ((e & K_MASK) == K_LITERAL) {
                         // up to three first-level entries (one or two literals each, <= 3 x LITLEN_BITS bits) leave
                         // more than the 15 valid bits the lookup after them may need
                         DROP(NB(e));
                         store16(op, (uint16_t)(e >> 16));
-                        op += 1 + ((e >> 12) & 1);
+                        op += (e >> 12) & 15;
                         e = LOOKUP_LITLEN();
                         if ((e & K_MASK) == K_LITERAL) {
                             DROP(NB(e));
                             store16(op, (uint16_t)(e >> 16));
-                            op += 1 + ((e >> 12) & 1);
+                            op += (e >> 12) & 15;
                             e = LOOKUP_LITLEN();
                             if ((e & K_MASK) == K_LITERAL) {
                                 DROP(NB(e));
                                 store16(op, (uint16_t)(e >> 16));
-                                op += 1 + ((e >> 12) & 1);
+                                op += (e >> 12) & 15;
                                 e = LOOKUP_LITLEN();
                             }
                         }
@@ -582,7 +621,7 @@ int Inflater::inflate_raw(const uint8_t *const in, const size_t in_len, uint8_t 
                     uint32_t length, distance;
                     if ((e & K_MASK) == K_MATCH) {
                         // length and distance code from one entry; only the distance's extra bits are left to read
-                        length = 3 + ((e >> 12) & 7);
+                        length = (e >> 12) & 15;
                         distance = (e >> 16) + (((uint32_t)bitbuf >> ((e >> 8) & 15)) & ((1u << (NB(e) - ((e >> 8) & 15))) - 1u));
                         DROP(NB(e));
                     } else {
@@ -644,6 +683,7 @@ int Inflater::inflate_raw(const uint8_t *const in, const size_t in_len, uint8_t 
                 } while (ip <= in_fast && op <= out_fast);
 #undef REFILL_FAST
 #undef LOOKUP_LITLEN
+#undef UNIFORM_STEP
                 if (block_done) break;
                 continue;       // re-evaluate: the careful loop below takes over near the ends
             }
@@ -670,7 +710,7 @@ int Inflater::inflate_raw(const uint8_t *const in, const size_t in_len, uint8_t 
             }
             uint32_t length, distance;
             if ((e & K_MASK) == K_MATCH) {
-                length = 3 + ((e >> 12) & 7);
+                length = (e >> 12) & 15;
                 distance = (e >> 16) + (((uint32_t)bitbuf >> ((e >> 8) & 15)) & ((1u << (NB(e) - ((e >> 8) & 15))) - 1u));
                 DROP(NB(e));
                 if (bitcnt < 0) { rc = fail(INF_TRUNCATED, "stream ends inside a block"); goto done; }
