@@ -99,6 +99,12 @@ class OracleEngine:
                                 self.pairs.append((k, t, int(w), d))
         return np.array(pts), np.array(cnts)
 
+    def count_async(self, first_slot, n_tiles, plane_order, edit_distance=2, hamming=False, mode=0, want_per_target=False):
+        self._pending = self.count(first_slot, n_tiles, plane_order, edit_distance, hamming, mode)
+
+    def count_fetch(self):
+        return self._pending
+
     def dup_pairs(self):
         return np.array(self.pairs, np.int32).reshape(-1, 4)
 

@@ -97,3 +97,44 @@ def test_lane_rows_are_the_sum_of_their_tiles():
     buf = flowcell.exchange_host(rows, np.arange(6), 2, 3, 11, None)
     assert np.array_equal(buf[:6], rows)
     assert np.array_equal(buf[6], rows[:3].sum(axis=0)) and np.array_equal(buf[7], rows[3:].sum(axis=0))
+
+
+def _driver_worker(rank, world, port, case, out_path):
+    """flowcell.count_rank_tiles (tile walk + staging pipeline) on each rank, with the oracle-backed
+    stand-in for the engine, then the all-reduce and the report as the driver does them."""
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port), RANK=str(rank), WORLD_SIZE=str(world))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from test_cli_host_logic import OracleEngine
+    from well_duplicates_b200 import count_cli, flowcell, reader, staging
+    from well_duplicates_b200.targets import load_targets
+    o = parse_count_args(case["args"])
+    lanes = o["lanes"].split(",")
+    tiles = count_cli.expected_tiles(o["stype"], o["tiles"])
+    wanted = [c for s, e in o["ranges"] for c in range(s, e)]
+    targets = load_targets(os.path.join(GOLDEN, case["targets"]), levels=o["levels"] + 1, limit=o["limit"])
+    eng = OracleEngine()
+    eng.load_targets(*targets.to_csr(o["levels"]), o["levels"])
+    rd = reader.BCLReader(os.path.join(GOLDEN, case["run"]), engine=eng)
+    st = staging.Stager(pinned=False, threads=2, cbcl_cache=rd._cbcl_cache)
+    mine = flowcell.plan(len(lanes), len(tiles), rank, world)
+    rows = flowcell.count_rank_tiles(eng, rd, st, lanes, tiles, mine, wanted, o["levels"], o["edit"], o["hamming"])
+    st.close()
+    buf = flowcell.exchange_host(rows, mine, len(lanes), len(tiles), 1 + 5 * o["levels"], dist)
+    text = io.StringIO()
+    flowcell.print_reports(text, lanes, tiles, buf, len(targets), o["levels"], verbose=not o["summary"])
+    with open("%s.%d" % (out_path, rank), "w") as fh:
+        fh.write(text.getvalue())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("name", ["two_lanes", "lev_default", "cbcl_default"])
+def test_two_rank_driver_loop_reproduces_reference_report(name, tmp_path):
+    case = [c for c in MAN["count"] if c["name"] == name][0]
+    out = str(tmp_path / "report")
+    mp.spawn(_driver_worker, args=(2, _free_port(), case, out), nprocs=2, join=True)
+    with open(os.path.join(GOLDEN, "count", name + ".stdout")) as fh:
+        want = fh.read()
+    for rank in (0, 1):
+        with open("%s.%d" % (out, rank)) as fh:
+            assert fh.read() == want

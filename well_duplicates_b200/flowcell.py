@@ -80,6 +80,31 @@ def print_reports(stream, lanes, tiles, buf, sample_size, levels, verbose):
         write_report(stream, lane, sample_size, [tiles[k] for k in order], [rows[k] for k in order], levels, verbose)
 
 
+def count_rank_tiles(eng, rd, stager, lanes, tiles, mine, wanted, levels, edit_distance, hamming, say=None):
+    """Counter rows [len(mine), 1 + 5 * levels] of this rank's tiles (``mine`` = ordinals into lanes x tiles).
+    Files -> page-locked planes on native threads one batch ahead of the GPU (staging.py); the planes stay in
+    host memory and the fused kernel pulls the sectors it needs (wd_tile_map_host)."""
+    from .staging import lane_batches
+    rows = np.zeros((len(mine), 1 + 5 * levels), dtype=np.int64)
+    names = ["%s/%s" % (lanes[int(o) // len(tiles)], tiles[int(o) % len(tiles)]) for o in mine]
+
+    def open_tile(name):
+        lane, tile = name.split("/")
+        return rd.get_tile(lane, tile)
+
+    k = 0
+    for got, staged in lane_batches(stager, open_tile, names, wanted):
+        for name in got:
+            lane, tile = name.split("/")
+            if say is not None:
+                say("Reading tile %s in lane %s" % (tile, lane))
+        plane_of = stager.deliver(eng, staged, first_slot=0, zero_copy=True)
+        eng.count_async(0, len(got), [plane_of[c] for c in wanted], edit_distance, hamming, mode=0)
+        rows[k:k + len(got)] = eng.count_fetch()[1]
+        k += len(got)
+    return rows
+
+
 def main(argv=None):
     import torch
     import torch.distributed as dist
@@ -122,28 +147,12 @@ def main(argv=None):
 
     mine = plan(len(lanes), len(tiles), rank, world)
     width = 1 + 5 * args.level
-    rows = np.zeros((len(mine), width), dtype=np.int64)
-    # This rank's tiles, lane after lane: files -> page-locked planes on native threads one batch ahead
-    # of the GPU (staging.py); the planes stay in host memory and the fused kernel pulls the sectors
-    # it needs (wd_tile_map_host).
-    from .staging import Stager, lane_batches
+    from .staging import Stager
     stager = Stager(threads=max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world)))),
                     cbcl_cache=rd._cbcl_cache)
-    names = ["%s/%s" % (lanes[int(o) // len(tiles)], tiles[int(o) % len(tiles)]) for o in mine]
-
-    def open_tile(name):
-        lane, tile = name.split("/")
-        return rd.get_tile(lane, tile)
-
-    k = 0
     with torch.cuda.stream(stream):
-        for got, staged in lane_batches(stager, open_tile, names, wanted):
-            for name in got:
-                say("Reading tile %s in lane %s" % tuple(reversed(name.split("/"))))
-            plane_of = stager.deliver(eng, staged, first_slot=0, zero_copy=True)
-            eng.count_async(0, len(got), [plane_of[c] for c in wanted], args.edit_distance, args.hamming, mode=0)
-            rows[k:k + len(got)] = eng.count_fetch()[1]
-            k += len(got)
+        rows = count_rank_tiles(eng, rd, stager, lanes, tiles, mine, wanted, args.level, args.edit_distance,
+                                args.hamming, say)
     stager.close()
     buf = exchange_host(rows, mine, len(lanes), len(tiles), width, dist if world > 1 else None) if world == 1 else None
     if world > 1:
