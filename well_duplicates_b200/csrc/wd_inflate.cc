@@ -384,7 +384,7 @@ inline uint64_t load64(const uint8_t *p) {
 // Two builds of the decoder, picked once at load time (ifunc): with BMI2 the variable shifts of the
 // bit buffer are SHRX / SHLX (no shuffling through CL, no flag dependency) -- 15-20 % on the
 // branch-free step, whose cost is its instruction count.
-#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__)
+#if defined(__x86_64__) && defined(__GNUC__) && !defined(__clang__) && !defined(WD_INFLATE_NO_MULTIVERSION)
 __attribute__((target_clones("default", "bmi2")))
 #endif
 int Inflater::inflate_raw(const uint8_t *const in, const size_t in_len, uint8_t *const out, const size_t out_cap,
