@@ -569,36 +569,50 @@ int Inflater::inflate_raw(const uint8_t *const in, const size_t in_len, uint8_t 
 // Blocks that mix literals and short matches (every base-call plane): which of the two comes next
 // is a coin toss per symbol, and a mispredicted branch costs more than either.  Literal entries (one
 // or two bytes) and fused match entries have one shape -- bits to drop, bytes produced, 16 payload
-// bits -- so one step serves both without a branch: a 16-byte copy from `op - distance` to `op` for a
-// match, from a scratch block onto itself for a literal, and the literal bytes stored to `op` or to
-// scratch.  Only what is rare branches: a distance below 16 (the 16-byte copy would overlap) or
-// beyond the start of the output.
-#define UNIFORM_STEP()                                                                                              \
+// bits -- so one step serves both without a branch: the payload is stored as two literal bytes, then
+// 16 bytes are copied -- for a match from `op - distance` over them, for a literal from a block of
+// zeros to just behind them (overwritten by the next symbol).  The step is bound by its instruction
+// count (no store-to-load forwarding, no loop-carried memory dependency).  Only what is rare
+// branches: a distance below 16 (the 16-byte copy would overlap) and, during the first 32 KB of
+// output, a distance that reaches in front of it.
+#define UNIFORM_STEP(FAR_OK)                                                                                        \
     {                                                                                                               \
-        const uint32_t is_match = (e >> 7) & 1u;                                                                    \
-        const uint32_t pos = (e >> 8) & 15u, nb = NB(e);                                                            \
+        const uint32_t nb = e & 63u;             /* bits 5 and 6 are clear in both kinds */                         \
+        const uint32_t pos = (e >> 8) & 15u;                                                                        \
         const uint32_t payload = e >> 16;                                                                           \
-        const uint32_t distance = payload + (((uint32_t)bitbuf >> pos) & ((1u << (nb - pos)) - 1u));                \
-        const uint32_t adv = (e >> 12) & 15u;                                                                       \
-        DROP(nb);                                                                                                   \
+        const uint32_t distance = payload + (((uint32_t)bitbuf & ((1u << nb) - 1u)) >> pos);                        \
+        const uintptr_t adv = (e >> 12) & 15u;                                                                      \
+        const uintptr_t m = (uintptr_t)(intptr_t)((int32_t)(e << 24) >> 31);      /* all ones for a match */        \
+        bitbuf >>= nb;                                                                                              \
+        bitcnt -= (int)nb;                                                                                          \
         e = LOOKUP_LITLEN();                                                                                        \
-        const uint32_t rare = is_match & ((uint32_t)(distance < 16) | (uint32_t)(distance > (size_t)(op - out)));  \
-        if (__builtin_expect(rare, 0)) {                                                                            \
-            if (distance > (size_t)(op - out)) { rc = fail(INF_BAD_DATA, "invalid distance too far back"); goto done; } \
-            for (uint32_t k = 0; k < adv; ++k) op[k] = op[(ptrdiff_t)k - (ptrdiff_t)distance];                      \
+        if (__builtin_expect(distance < 16 || (!(FAR_OK) && distance > (size_t)(op - out)), 0)) {                   \
+            if (m) {                                                                                                \
+                if (distance > (size_t)(op - out)) { rc = fail(INF_BAD_DATA, "invalid distance too far back"); goto done; } \
+                for (uintptr_t k = 0; k < adv; ++k) op[k] = op[(ptrdiff_t)k - (ptrdiff_t)distance];                 \
+            } else {                                                                                                \
+                store16(op, (uint16_t)payload);                                                                     \
+            }                                                                                                       \
         } else {                                                                                                    \
-            const uintptr_t m = (uintptr_t)0 - (uintptr_t)is_match;                                                 \
+            store16(op, (uint16_t)payload);                                                                         \
             const uintptr_t su = (uintptr_t)scratch, ou = (uintptr_t)op;                                            \
-            memcpy((uint8_t *)(su + ((ou - su) & m)), (const uint8_t *)(su + ((ou - distance - su) & m)), 16);      \
-            store16((uint8_t *)(ou + ((su + 16 - ou) & m)), (uint16_t)payload);                                     \
+            memcpy((uint8_t *)(ou + (adv & ~m)), (const uint8_t *)(su + ((ou - distance - su) & m)), 16);           \
         }                                                                                                           \
         op += adv;                                                                                                  \
     }
-                alignas(16) uint8_t scratch[32] = {0};
+                alignas(16) static const uint8_t scratch[16] = {0};
+                // every distance a stream can code reaches back at most 32768 bytes: beyond that much output only
+                // distances below 16 need a second look
+                const bool far_ok = op - out >= 32768;
                 do {
                     if (uniform && (e & (3u << 5)) == 0) {          // K_LITERAL or K_MATCH
-                        UNIFORM_STEP();                             // <= 23 bits each: two fit one refill
-                        if ((e & (3u << 5)) == 0) UNIFORM_STEP();
+                        if (far_ok) {
+                            UNIFORM_STEP(true);                     // <= 23 bits each: two fit one refill
+                            if ((e & (3u << 5)) == 0) UNIFORM_STEP(true);
+                        } else {
+                            UNIFORM_STEP(false);
+                            if ((e & (3u << 5)) == 0) UNIFORM_STEP(false);
+                        }
                         REFILL_FAST();
                         continue;
                     }
