@@ -190,7 +190,6 @@ def host_inflate_sample(plane, threads, seconds=4.0):
     inflate (wd_inflate_batch, csrc/wd_inflate.cc -- what staging.Stager runs) on .bcl.gz-shaped members
     (one compressed plane of the benchmark tile) on all host threads, and zlib -- what the reference's
     gzip.open().read() runs -- on the same members."""
-    import ctypes
     import zlib
     from well_duplicates_b200 import _lib
     raw = struct_header(plane.size) + plane.tobytes()

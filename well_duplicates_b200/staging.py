@@ -20,7 +20,6 @@ reader (bcl_direct_reader.py:200-216 BCL first, CBCL on FileNotFoundError;
 The CBCL header and tile table are parsed once per file (CbclFile), not once per
 tile and cycle as bcl_direct_reader.py:261-292 does.
 """
-import ctypes as C
 import os
 import struct
 from concurrent.futures import ThreadPoolExecutor
