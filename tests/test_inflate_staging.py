@@ -368,3 +368,214 @@ def test_inflate_under_address_and_ub_sanitizers(tmp_path):
     run = subprocess.run([exe] + files, capture_output=True, text=True, timeout=600)
     assert run.returncode == 0, run.stdout + run.stderr
     assert "fuzz runs 2000" in run.stdout
+
+
+# ---- deflate streams zlib's own compressor never writes -------------------------------------------
+class _BitWriter:
+    def __init__(self):
+        self.acc, self.n, self.out = 0, 0, bytearray()
+
+    def bits(self, value, count):                 # LSB first (header fields, extra bits)
+        self.acc |= value << self.n
+        self.n += count
+        while self.n >= 8:
+            self.out.append(self.acc & 0xff)
+            self.acc >>= 8
+            self.n -= 8
+
+    def code(self, code, length):                 # Huffman codes go MSB first
+        self.bits(int(format(code, "0%db" % length)[::-1], 2), length)
+
+    def done(self):
+        if self.n:
+            self.out.append(self.acc & 0xff)
+        return bytes(self.out)
+
+
+_LEN_BASE = [3, 4, 5, 6, 7, 8, 9, 10, 11, 13, 15, 17, 19, 23, 27, 31, 35, 43, 51, 59, 67, 83, 99, 115, 131, 163, 195, 227, 258]
+_LEN_EXTRA = [0, 0, 0, 0, 0, 0, 0, 0, 1, 1, 1, 1, 2, 2, 2, 2, 3, 3, 3, 3, 4, 4, 4, 4, 5, 5, 5, 5, 0]
+_DIST_BASE = [1, 2, 3, 4, 5, 7, 9, 13, 17, 25, 33, 49, 65, 97, 129, 193, 257, 385, 513, 769, 1025, 1537, 2049, 3073, 4097, 6145,
+              8193, 12289, 16385, 24577]
+_DIST_EXTRA = [0, 0, 0, 0, 1, 1, 2, 2, 3, 3, 4, 4, 5, 5, 6, 6, 7, 7, 8, 8, 9, 9, 10, 10, 11, 11, 12, 12, 13, 13]
+
+
+def _huffman_lengths(freq, limit=15):
+    """Code lengths of a Huffman code for the symbols with freq > 0 (complete by construction);
+    frequencies are flattened until no code is longer than ``limit``."""
+    import heapq
+    freq = list(freq)
+    while True:
+        heap = [(f, i, (i,)) for i, f in enumerate(freq) if f > 0]
+        lens = [0] * len(freq)
+        if len(heap) == 1:
+            lens[heap[0][1]] = 1
+            return lens
+        heapq.heapify(heap)
+        tick = len(freq)
+        while len(heap) > 1:
+            a, b = heapq.heappop(heap), heapq.heappop(heap)
+            for s in a[2] + b[2]:
+                lens[s] += 1
+            heapq.heappush(heap, (a[0] + b[0], tick, a[2] + b[2]))
+            tick += 1
+        if max(lens) <= limit:
+            return lens
+        freq = [(f + 1) // 2 + 1 if f > 0 else 0 for f in freq]
+
+
+def _canonical(lens):
+    codes, code = {}, 0
+    for length in range(1, 16):
+        for s, l in enumerate(lens):
+            if l == length:
+                codes[s] = (code, length)
+                code += 1
+        code <<= 1
+    return codes
+
+
+def _tokens(rnd, data, p_match):
+    """Greedy-random LZ77 parse: any earlier occurrence within 32768 bytes, any length up to 258,
+    including overlapping copies and distances of 1..15."""
+    seen, pos, out = {}, 0, []
+    while pos < len(data):
+        key = data[pos:pos + 3]
+        cands = [c for c in seen.get(key, ()) if pos - c <= 32768]
+        if len(key) == 3 and cands and rnd.random() < p_match:
+            src = rnd.choice(cands[-8:] + cands[:2])
+            length = 3
+            while length < 258 and pos + length < len(data) and data[src + length] == data[pos + length]:
+                length += 1
+            length = rnd.randint(3, length)
+            out.append((length, pos - src))
+        else:
+            out.append(data[pos])
+            length = 1
+        for k in range(pos, pos + length):
+            seen.setdefault(data[k:k + 3], []).append(k)
+        pos += length
+    return out
+
+
+def _sym_of(value, base):
+    s = 0
+    while s + 1 < len(base) and base[s + 1] <= value:
+        s += 1
+    return s
+
+
+def _encode_dynamic(w, tokens, final, skew):
+    lit_freq, dist_freq = [0] * 286, [0] * 30
+    for t in tokens:
+        if isinstance(t, tuple):
+            lit_freq[257 + _sym_of(t[0], _LEN_BASE)] += 1
+            dist_freq[_sym_of(t[1], _DIST_BASE)] += 1
+        else:
+            lit_freq[t] += 1
+    lit_freq[256] = 1
+    if skew:                                       # stretch the code: rare symbols get the longest codes allowed
+        lit_freq = [f ** 3 if f else 0 for f in lit_freq]
+        dist_freq = [f ** 3 if f else 0 for f in dist_freq]
+    if not any(dist_freq):
+        dist_freq[0] = 1
+    ll, dl = _huffman_lengths(lit_freq), _huffman_lengths(dist_freq)
+    n_lit = max(257, max(i for i, l in enumerate(ll) if l) + 1)
+    n_dist = max(1, max(i for i, l in enumerate(dl) if l) + 1)
+    w.bits(1 if final else 0, 1)
+    w.bits(2, 2)
+    w.bits(n_lit - 257, 5)
+    w.bits(n_dist - 1, 5)
+    w.bits(19 - 4, 4)
+    # code-length code: a complete code over the 19 symbols (13 of 4 bits, 6 of 5 bits), no run-length symbols used
+    pre_lens = [5, 5, 5] + [4] * 13 + [5, 5, 5]    # symbols 16, 17, 18, 0..15 -> indexed by symbol below
+    by_symbol = {16: 5, 17: 5, 18: 5}
+    by_symbol.update({s: 4 for s in range(13)})
+    by_symbol.update({13: 5, 14: 5, 15: 5})
+    order = [16, 17, 18, 0, 8, 7, 9, 6, 10, 5, 11, 4, 12, 3, 13, 2, 14, 1, 15]
+    for s in order:
+        w.bits(by_symbol[s], 3)
+    pre = _canonical([by_symbol[s] for s in range(19)])
+    for l in ll[:n_lit] + dl[:n_dist]:
+        w.code(*pre[l])
+    lit, dist = _canonical(ll), _canonical(dl)
+    for t in tokens:
+        if isinstance(t, tuple):
+            ls = _sym_of(t[0], _LEN_BASE)
+            w.code(*lit[257 + ls])
+            w.bits(t[0] - _LEN_BASE[ls], _LEN_EXTRA[ls])
+            ds = _sym_of(t[1], _DIST_BASE)
+            w.code(*dist[ds])
+            w.bits(t[1] - _DIST_BASE[ds], _DIST_EXTRA[ds])
+        else:
+            w.code(*lit[t])
+    w.code(*lit[256])
+    del pre_lens
+
+
+def _encode_fixed(w, tokens, final):
+    ll = [8] * 144 + [9] * 112 + [7] * 24 + [8] * 8
+    lit, dist = _canonical(ll), {s: (s, 5) for s in range(30)}
+    w.bits(1 if final else 0, 1)
+    w.bits(1, 2)
+    for t in tokens:
+        if isinstance(t, tuple):
+            ls = _sym_of(t[0], _LEN_BASE)
+            w.code(*lit[257 + ls])
+            w.bits(t[0] - _LEN_BASE[ls], _LEN_EXTRA[ls])
+            ds = _sym_of(t[1], _DIST_BASE)
+            w.code(*dist[ds])
+            w.bits(t[1] - _DIST_BASE[ds], _DIST_EXTRA[ds])
+        else:
+            w.code(*lit[t])
+    w.code(*lit[256])
+
+
+def test_streams_from_a_foreign_encoder(lib):
+    """Valid deflate that zlib's compressor never writes -- matches at the full 32768 distance and of
+    every length, overlapping copies at distances 1..15, 15-bit codes, empty blocks of all three
+    types in between, a match that crosses block boundaries' history -- decoded like zlib's inflate
+    decodes it."""
+    rnd = random.Random(12)
+    alphabet = bytes(rnd.sample(range(256), 40))
+    for trial in range(8):
+        n = rnd.choice([3000, 40000, 90000])
+        data = bytearray(rnd.choice(alphabet) for _ in range(n))
+        for _ in range(n // 400):                   # long repeats, some of them 32768 back, some runs
+            length = rnd.randint(3, 600)
+            dst = rnd.randrange(0, max(1, n - length))
+            back = rnd.choice([1, 2, 7, 15, 16, 17, 255, 4096, 32767, 32768])
+            if dst - back >= 0:
+                for k in range(length):
+                    data[dst + k] = data[dst + k - back]
+        data = bytes(data)
+        tokens = _tokens(rnd, data, p_match=rnd.choice([0.3, 0.9, 1.0]))
+        w = _BitWriter()
+        cuts = sorted(rnd.sample(range(1, len(tokens)), min(4, len(tokens) - 1))) + [len(tokens)]
+        start = 0
+        for bi, end in enumerate(cuts):
+            final = end == len(tokens)
+            kind = rnd.choice(["dyn", "dyn_skew", "fixed"])
+            if kind == "fixed":
+                _encode_fixed(w, tokens[start:end], final and bi % 2 == 0)
+            else:
+                _encode_dynamic(w, tokens[start:end], final and bi % 2 == 0, kind == "dyn_skew")
+            if not (final and bi % 2 == 0):
+                # an empty stored block (what Z_SYNC_FLUSH writes), then maybe an empty fixed block
+                w.bits(0, 1)
+                w.bits(0, 2)
+                if w.n:
+                    w.bits(0, 8 - w.n)
+                w.bits(0, 16)
+                w.bits(0xffff, 16)
+                if final:
+                    w.bits(1, 1)
+                    w.bits(1, 2)
+                    w.code(0, 7)                    # end-of-block in the fixed code
+            start = end
+        raw_deflate = w.done()
+        assert zlib.decompress(raw_deflate, wbits=-15) == data           # the stream is valid
+        framed = b"\x1f\x8b\x08\0" + bytes(6) + raw_deflate + struct.pack("<II", zlib.crc32(data), len(data))
+        rc, out = native_gunzip(lib, framed, len(data))
+        assert rc == 0 and out == data, (trial, rc, lib.wd_last_error())
+        rc, out = native_gunzip(lib, framed, len(data) - 1)
+        assert rc == _lib.WD_E_CAPACITY and out == data[:-1]
