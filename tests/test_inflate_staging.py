@@ -579,3 +579,34 @@ def test_streams_from_a_foreign_encoder(lib):
         assert rc == 0 and out == data, (trial, rc, lib.wd_last_error())
         rc, out = native_gunzip(lib, framed, len(data) - 1)
         assert rc == _lib.WD_E_CAPACITY and out == data[:-1]
+
+
+def test_inflate_batch_under_thread_sanitizer(tmp_path):
+    """wd_inflate_batch's native thread pool under -fsanitize=thread (tests/inflate_batch_tsan.cc)."""
+    import shutil
+    import subprocess
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    if shutil.which("g++") is None:
+        pytest.skip("no g++")
+    exe = str(tmp_path / "inflate_tsan")
+    built = subprocess.run(["g++", "-O1", "-g", "-std=c++17", "-fsanitize=thread", "-DWD_INFLATE_NO_MULTIVERSION", "-o", exe,
+                            os.path.join(root, "tests", "inflate_batch_tsan.cc"),
+                            os.path.join(root, "well_duplicates_b200", "csrc", "wd_inflate.cc"), "-lpthread"],
+                           capture_output=True, text=True)
+    if built.returncode != 0 and "tsan" in built.stderr.lower():
+        pytest.skip("sanitizer runtime not installed")
+    assert built.returncode == 0, built.stderr
+    rng = np.random.default_rng(2)
+    files, total = [], 0
+    for k in range(5):
+        raw = bcl_like(rng, 150000 + 1000 * k)
+        files.append(str(tmp_path / ("p%d.gz" % k)))
+        with open(files[-1], "wb") as fh:
+            fh.write(deflate(raw, 1 + k))
+    for k in range(64):
+        total += 150000 + 1000 * (k % 5)
+    run = subprocess.run([exe] + files, capture_output=True, text=True, timeout=600)
+    if run.returncode != 0 and "unexpected memory mapping" in run.stderr:
+        pytest.skip("ThreadSanitizer cannot map its shadow memory in this container")
+    assert run.returncode == 0 and "WARNING: ThreadSanitizer" not in run.stderr, run.stdout + run.stderr
+    assert "batch rc 0 total %d" % total in run.stdout
