@@ -157,3 +157,39 @@ def test_quiet_and_logged_runs_print_the_same_report(oracle_engine):
         outs.append(out.getvalue())
         assert (err.getvalue() == "") == bool(extra)
     assert outs[0] == outs[1] and outs[0]
+
+
+def test_batched_lane_with_mixed_tile_sizes_equals_the_reference_port(tmp_path, oracle_engine, monkeypatch):
+    """A lane of eight tiles of two sizes with a pinned budget that holds three tiles: the -q walk
+    of the smaller size (batches of 3, 1, 2, 2 host-mapped tiles) prints what the reference's loops print."""
+    from oracle import ref_port as R
+    from well_duplicates_b200 import synth
+    rng = np.random.default_rng(33)
+    run = str(tmp_path / "run")
+    row_len, ncyc = 60, 16
+    sizes = [5000, 5000, 5000, 5000, 6100, 6100, 6100, 6100]
+    tiles = ["11%02d" % (k + 1) for k in range(8)]
+    for name, n in zip(tiles, sizes):
+        td = synth.make_tile(rng, n, ncyc, row_len, pf_rate=0.7, dup_rate=0.3, shift_share=0.3, nocall_rate=0.01)
+        synth.write_bcl_tile(run, 3, int(name), td, compresslevel=int(rng.integers(1, 9)))
+    X, Y = synth.hex_lattice(5000, row_len)
+    centres = rng.choice(np.arange(1000, 4000), size=60, replace=False)
+    rings = [R.ring_indexes(X, Y, int(c)) for c in centres]
+    target_file = str(tmp_path / "targets.list")
+    with open(target_file, "w") as fh:
+        fh.write(R.target_file_text([int(c) for c in centres], rings))
+    want = R.count_run(run, target_file, "3", tiles, 5, [(2, 9), (11, 15)], edit_distance=2, verbose=True)
+    per_tile = 2 * 1 + 11 * staging._round_up(5000 + 4, 256) + staging._round_up(5000, 256)
+    monkeypatch.setattr(staging, "PINNED_BUDGET_BYTES", 3 * per_tile + 100)
+    batches = []
+    real_count = oracle_engine.count
+
+    def spy(first_slot, n_tiles, *a, **k):
+        batches.append(n_tiles)
+        return real_count(first_slot, n_tiles, *a, **k)
+    monkeypatch.setattr(oracle_engine, "count", spy)
+    out = io.StringIO()
+    with contextlib.redirect_stdout(out):
+        count_cli.main(["-f", target_file, "-r", run, "-s", "1108", "-i", "3", "-l", "5", "--cycles", "2-9,11-15", "-q"])
+    assert out.getvalue() == want
+    assert batches == [3, 1, 2, 2]          # the budget holds three 5000-well tiles or two 6100-well ones
