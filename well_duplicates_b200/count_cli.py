@@ -13,7 +13,6 @@ from .targets import load_targets
 __VERSION__ = 0.3
 HISEQ_4000 = "hiseq_4000"
 HISEQ_X = "hiseq_x"
-HBM_BUDGET_BYTES = 120 << 30     # planes kept resident per batch of tiles (flowcell driver, copy staging)
 
 
 def log(msg):
