@@ -6,6 +6,7 @@ the counter reduction run in the CUDA library."""
 import re
 import sys
 from argparse import ArgumentDefaultsHelpFormatter, ArgumentParser
+
 from . import reader as bcl_direct_reader
 from .report import dupl_from_per_target, output_writer
 from .targets import load_targets
