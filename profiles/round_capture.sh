@@ -7,4 +7,6 @@ bash profiles/capture.sh > $O/capture.log 2>&1
 python profiles/measure_configs.py --configs 4,3,5 > $O/configs.jsonl 2> $O/configs.err
 bash profiles/capture_exhaustive.sh > $O/capture_exh.log 2>&1
 python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_ref.json 2> $O/bench_ref.err
-tail -c 1500 $O/bench_n1.json; echo; cat $O/configs.jsonl | cut -c1-600; tail -2 $O/bench_ref.json | cut -c1-400
+# a lane from .filter/.bcl.gz files on disk to counters (staging pipeline)
+python profiles/measure_files_e2e.py --tiles 32 --distinct 8 > $O/files_e2e.json 2> $O/files_e2e.err; rm -rf /tmp/wd_run
+tail -c 1500 $O/bench_n1.json; echo; cat $O/configs.jsonl | cut -c1-600; tail -2 $O/bench_ref.json | cut -c1-400; cut -c1-700 $O/files_e2e.json
