@@ -193,3 +193,50 @@ def test_batched_lane_with_mixed_tile_sizes_equals_the_reference_port(tmp_path, 
         count_cli.main(["-f", target_file, "-r", run, "-s", "1108", "-i", "3", "-l", "5", "--cycles", "2-9,11-15", "-q"])
     assert out.getvalue() == want
     assert batches == [3, 1, 2, 2]          # the budget holds three 5000-well tiles or two 6100-well ones
+
+
+@pytest.mark.parametrize("case", MAN["count"], ids=lambda c: c["name"])
+def test_quiet_run_prints_the_reference_report_from_counter_rows(case, oracle_engine):
+    """With -q the report is written straight from the counter rows of the device reduction
+    (report.write_report) instead of the per-target lists: same stdout as the reference for every
+    golden case -- the stdout of count_well_duplicates.py does not depend on -q -- including the lane
+    without hits that ends in ZeroDivisionError after its per-tile lines."""
+    with open(os.path.join(GOLDEN, "count", case["name"] + ".stdout")) as fh:
+        want_out = fh.read()
+    argv = ["-f", os.path.join(GOLDEN, case["targets"]), "-r", os.path.join(GOLDEN, case["run"])] + case["args"]
+    if "-q" not in argv:
+        argv.append("-q")
+    out, err = io.StringIO(), io.StringIO()
+    with contextlib.redirect_stdout(out), contextlib.redirect_stderr(err):
+        if case["returncode"] != 0:
+            with pytest.raises(ZeroDivisionError):
+                count_cli.main(argv)
+        else:
+            count_cli.main(argv)
+    assert out.getvalue() == want_out and err.getvalue() == ""
+    assert set(oracle_engine.calls) == {"map"}
+
+
+def test_quiet_lane_without_any_valid_target(tmp_path, oracle_engine):
+    """No centre passes the filter anywhere in the lane: the reference's output_writer never learns the
+    level count and prints the summary without level lines (count_well_duplicates.py:41-47, :124-125)."""
+    from oracle import ref_port as R
+    from well_duplicates_b200 import synth
+    rng = np.random.default_rng(4)
+    run = str(tmp_path / "run")
+    for name in ("1101", "1102"):
+        td = synth.make_tile(rng, 3000, 8, 50, pf_rate=0.5)
+        td.filt[:] = 0
+        synth.write_bcl_tile(run, 1, int(name), td)
+    X, Y = synth.hex_lattice(3000, 50)
+    centres = [700, 1500, 2100]
+    target_file = str(tmp_path / "targets.list")
+    with open(target_file, "w") as fh:
+        fh.write(R.target_file_text(centres, [R.ring_indexes(X, Y, c) for c in centres]))
+    want = R.count_run(run, target_file, "1", ["1101", "1102"], 3, [(0, 8)], verbose=True)
+    assert "Level" not in want and "0.00%" in want
+    for flags in ([], ["-q"]):
+        out, err = io.StringIO(), io.StringIO()
+        with contextlib.redirect_stdout(out), contextlib.redirect_stderr(err):
+            count_cli.main(["-f", target_file, "-r", run, "-s", "1102", "-i", "1", "--cycles", "0-8"] + flags)
+        assert out.getvalue() == want

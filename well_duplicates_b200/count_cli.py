@@ -8,7 +8,7 @@ import sys
 from argparse import ArgumentDefaultsHelpFormatter, ArgumentParser
 
 from . import reader as bcl_direct_reader
-from .report import dupl_from_per_target, output_writer
+from .report import dupl_from_per_target, output_writer, write_report
 from .targets import load_targets
 
 __VERSION__ = 0.3
@@ -132,7 +132,7 @@ def main(argv=None):
     stager = bcl_direct_reader.default_stager(bcl_reader._cbcl_cache)
 
     for lane in lanes:
-        lane_dupl = {}
+        lane_dupl, lane_rows = {}, {}
         # Files -> page-locked planes on native threads, one batch ahead of the GPU (staging.py).
         # -q: many tiles per launch, planes stay in host memory and the fused kernel pulls the
         # sectors it needs.  Otherwise one tile at a time, in the reference's log order, planes
@@ -143,8 +143,14 @@ def main(argv=None):
             plane_of = stager.deliver(eng, staged, first_slot=0, zero_copy=args.quiet)
             order = [plane_of[c] for c in wanted]
             say("Got %i sequences from %i contiguous cycle ranges." % (n_unique * len(cycles), len(cycles)))
+            if args.quiet:
+                # nothing to log: the counter rows of the device reduction are the report (report.write_report)
+                _, counters = eng.count(0, len(names), order, args.edit_distance, args.hamming, mode=0, per_target=False)
+                for k, tname in enumerate(names):
+                    lane_rows[tname] = counters[k]
+                continue
             per_target, _ = eng.count(0, len(names), order, args.edit_distance, args.hamming, mode=mode, per_target=True)
-            pairs = eng.dup_pairs() if mode == 1 else ()
+            pairs = eng.dup_pairs()
             for k, tname in enumerate(names):
                 lane_dupl[tname] = dupl_from_per_target(per_target[k], args.level)
                 rows = [r for r in pairs if r[0] == k]
@@ -157,6 +163,13 @@ def main(argv=None):
                         say("center seq at {:>07}: {}".format(c, seq[c]))
                         say("well seq at   {:>07}: {}".format(int(well), seq[int(well)]))
                         say("edit distance: {}".format(int(dist)))
+        if args.quiet:
+            names = sorted(lane_rows)
+            # output_writer infers the level count from the first tile with a valid target: none -> no level lines
+            levels = args.level if any(int(lane_rows[t][0]) for t in names) else 0
+            write_report(sys.stdout, lane, len(targets), names, [lane_rows[t][:1 + 5 * levels] for t in names], levels,
+                         verbose=not args.summary_only)
+            continue
         output_writer(lane, len(targets), lane_dupl, verbose=not args.summary_only)
 
 
