@@ -131,28 +131,52 @@ def main(argv=None):
     from .staging import lane_batches
     stager = bcl_direct_reader.default_stager(bcl_reader._cbcl_cache)
 
-    for lane in lanes:
-        lane_dupl, lane_rows = {}, {}
-        # Files -> page-locked planes on native threads, one batch ahead of the GPU (staging.py).
-        # -q: many tiles per launch, planes stay in host memory and the fused kernel pulls the
-        # sectors it needs.  Otherwise one tile at a time, in the reference's log order, planes
-        # copied to HBM for the two-pass kernels that feed the duplicate-pair log.
-        for names, staged in lane_batches(stager, lambda t: bcl_reader.get_tile(lane, t), tiles, wanted,
-                                          per_batch=None if args.quiet else 1,
-                                          announce=lambda t: say("Reading tile %s in lane %s" % (t, lane))):
-            plane_of = stager.deliver(eng, staged, first_slot=0, zero_copy=args.quiet)
-            order = [plane_of[c] for c in wanted]
-            say("Got %i sequences from %i contiguous cycle ranges." % (n_unique * len(cycles), len(cycles)))
-            if args.quiet:
-                # nothing to log: the counter rows of the device reduction are the report (report.write_report)
-                _, counters = eng.count(0, len(names), order, args.edit_distance, args.hamming, mode=0, per_target=False)
-                for k, tname in enumerate(names):
-                    lane_rows[tname] = counters[k]
-                continue
+    # Files -> page-locked planes on native threads, one batch ahead of the GPU (staging.py), across
+    # lane boundaries: the first tiles of the next lane inflate while this lane is finished and printed.
+    # -q: many tiles per launch, planes stay in host memory and the fused kernel pulls the sectors
+    # it needs.  Otherwise one tile at a time, in the reference's log order, planes copied to HBM
+    # for the two-pass kernels that feed the duplicate-pair log.
+    lanes = [str(lane) for lane in lanes]
+    walk = ["%s/%s" % (lane, t) for lane in lanes for t in tiles]
+    lane_dupl = {lane: {} for lane in lanes}      # per-target lists (log mode), as the reference builds them
+    lane_rows = {lane: {} for lane in lanes}      # counter rows of the device reduction (-q)
+    todo = {lane: len(tiles) for lane in lanes}
+
+    def open_tile(name):
+        lane, t = name.split("/")
+        return bcl_reader.get_tile(lane, t)
+
+    def announce(name):
+        lane, t = name.split("/")
+        say("Reading tile %s in lane %s" % (t, lane))
+
+    def finish(lane):
+        if not args.quiet:
+            output_writer(lane, len(targets), lane_dupl[lane], verbose=not args.summary_only)
+            return
+        names = sorted(lane_rows[lane])
+        # output_writer infers the level count from the first tile with a valid target: none -> no level lines
+        levels = args.level if any(int(lane_rows[lane][t][0]) for t in names) else 0
+        write_report(sys.stdout, lane, len(targets), names, [lane_rows[lane][t][:1 + 5 * levels] for t in names], levels,
+                     verbose=not args.summary_only)
+
+    for names, staged in lane_batches(stager, open_tile, walk, wanted, per_batch=None if args.quiet else 1,
+                                      announce=announce):
+        plane_of = stager.deliver(eng, staged, first_slot=0, zero_copy=args.quiet)
+        order = [plane_of[c] for c in wanted]
+        say("Got %i sequences from %i contiguous cycle ranges." % (n_unique * len(cycles), len(cycles)))
+        if args.quiet:
+            # nothing to log: the counter rows of the device reduction are the report (report.write_report)
+            _, counters = eng.count(0, len(names), order, args.edit_distance, args.hamming, mode=0, per_target=False)
+        else:
             per_target, _ = eng.count(0, len(names), order, args.edit_distance, args.hamming, mode=mode, per_target=True)
             pairs = eng.dup_pairs()
-            for k, tname in enumerate(names):
-                lane_dupl[tname] = dupl_from_per_target(per_target[k], args.level)
+        for k, name in enumerate(names):
+            lane, tname = name.split("/")
+            if args.quiet:
+                lane_rows[lane][tname] = counters[k]
+            else:
+                lane_dupl[lane][tname] = dupl_from_per_target(per_target[k], args.level)
                 rows = [r for r in pairs if r[0] == k]
                 if rows:
                     wells = sorted({int(centres[r[1]]) for r in rows} | {int(r[2]) for r in rows})
@@ -163,15 +187,12 @@ def main(argv=None):
                         say("center seq at {:>07}: {}".format(c, seq[c]))
                         say("well seq at   {:>07}: {}".format(int(well), seq[int(well)]))
                         say("edit distance: {}".format(int(dist)))
-        if args.quiet:
-            names = sorted(lane_rows)
-            # output_writer infers the level count from the first tile with a valid target: none -> no level lines
-            levels = args.level if any(int(lane_rows[t][0]) for t in names) else 0
-            write_report(sys.stdout, lane, len(targets), names, [lane_rows[t][:1 + 5 * levels] for t in names], levels,
-                         verbose=not args.summary_only)
-            continue
-        output_writer(lane, len(targets), lane_dupl, verbose=not args.summary_only)
-
+            todo[lane] -= 1
+            if todo[lane] == 0:
+                finish(lane)
+    if not tiles:
+        for lane in lanes:
+            finish(lane)
 
 if __name__ == "__main__":
     main()
