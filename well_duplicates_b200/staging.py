@@ -98,7 +98,9 @@ class Stager:
     def __init__(self, pinned=True, threads=None, cbcl_cache=None):
         self._lib = _lib.load()
         self.blocks = [HostBlock(pinned), HostBlock(pinned)]
-        self.threads = int(threads if threads else int(os.environ.get("WELLDUP_INFLATE_THREADS", "0")) or (os.cpu_count() or 1))
+        # default: the cores this process may run on (affinity mask / cgroup), not every core of the box
+        usable = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+        self.threads = int(threads if threads else int(os.environ.get("WELLDUP_INFLATE_THREADS", "0")) or usable)
         self._cbcl_cache = {} if cbcl_cache is None else cbcl_cache
         self._worker = ThreadPoolExecutor(max_workers=1)
 
