@@ -35,7 +35,7 @@
 extern "C" {
 #endif
 
-#define WD_ABI_VERSION 1
+#define WD_ABI_VERSION 2
 
 #if defined(__GNUC__)
 #define WD_API __attribute__((visibility("default")))
@@ -87,6 +87,17 @@ WD_API int wd_set_l2_fetch_granularity(wd_ctx *ctx, int bytes, int *previous);
 WD_API int wd_last_count_h2d_bytes(wd_ctx *ctx, uint64_t *out);
 /* Number of kernel launches issued by this context so far (bench.py gpu_launches). */
 WD_API int wd_launch_count(wd_ctx *ctx, uint64_t *out);
+/* Knobs of wd_count for measurement sweeps (profiles/): 0 (or -1 where noted) leaves the library's choice.
+ * NULL restores every default.  The library reads no environment variables. */
+typedef struct wd_tuning {
+    int32_t step0, step1;  /* cycles the fused kernel reads per round (first round, later rounds), 1..8 */
+    int32_t centre_chunk;  /* centre cycles decoded per warp-wide load: 8, 16 or 32 */
+    int32_t head_planes;   /* host-mapped tiles: compared positions whose planes are copied to HBM by DMA, 0..8; -1 default */
+    int32_t head_groups;   /* ... in how many tile groups, pipelined against the counting kernels */
+    int32_t visit_order;   /* 0: targets in list order; 1 or -1: in ascending order of their centre well */
+    int32_t reserved[10];
+} wd_tuning;
+WD_API int wd_set_tuning(wd_ctx *ctx, const wd_tuning *tuning);
 
 /* ---- stage 1: neighbourhood construction ----------------------------------
  * Replaces yield_coords + get_indexes of prepare_cluster_indexes.py
@@ -162,8 +173,14 @@ WD_API int wd_get_seqs(wd_ctx *ctx, int tile_slot, const int64_t *indices, uint3
  *   tile_counters[n_tiles][1+5*levels] int64: Targets, then per level
  *                Wells, Dups, Hit, AccO, AccI.
  * edit_distance / hamming are -e / --hamming (:200, :257).
- * mode: 0 = fused gather+compare kernel, 1 = two-pass (K4/K5 packed words in
- * HBM, then K6).  Both give identical results. */
+ * mode: WD_MODE_FUSED = fused gather+compare kernel, WD_MODE_TWO_PASS = K4/K5 packed
+ * words in HBM, then K6 (also logs), WD_MODE_FUSED_LOG = the fused kernel, and every
+ * duplicate pair is logged for wd_dup_pairs (count_well_duplicates.py:258-262).  All
+ * three give identical counters.  A target with an empty ring whose centre passes the
+ * filter of a counted tile gives WD_E_ASSERT (:249) when the results are fetched. */
+#define WD_MODE_FUSED 0
+#define WD_MODE_TWO_PASS 1
+#define WD_MODE_FUSED_LOG 2
 WD_API int wd_count(wd_ctx *ctx, int first_slot, int n_tiles, const int32_t *plane_order, int seq_len,
              int edit_distance, int hamming, int mode,
              int32_t *per_target, int64_t *tile_counters);
@@ -172,19 +189,57 @@ WD_API int wd_count(wd_ctx *ctx, int first_slot, int n_tiles, const int32_t *pla
 WD_API int wd_count_async(wd_ctx *ctx, int first_slot, int n_tiles, const int32_t *plane_order,
                    int seq_len, int edit_distance, int hamming, int mode, int want_per_target);
 WD_API int wd_count_fetch(wd_ctx *ctx, int32_t *per_target, int64_t *tile_counters);
-/* Duplicate pairs of the last two-pass wd_count (count_well_duplicates.py:258-262):
- * rows of (tile, target ordinal, well, distance), in reference log order. */
+/* Duplicate pairs of the last wd_count in mode 1 or 2 (count_well_duplicates.py:258-262):
+ * rows of (tile of the batch, target ordinal, well, distance), in reference log order
+ * (tile; then target, level, well as listed).  *n_rows is always set; WD_E_CAPACITY when
+ * cap is too small.  Every pair is delivered however many there are: if the device-side
+ * log was too small the library grows it and repeats the count (the tile slots must still
+ * hold their planes, i.e. call this before staging the next batch). */
 WD_API int wd_dup_pairs(wd_ctx *ctx, int32_t *rows /* cap x 4 */, size_t cap, uint64_t *n_rows);
+/* Same, plus the two sequences of every pair as the reference prints them (:260-261):
+ * codes[row][0] = centre, codes[row][1] = ring well, seq_len bytes each, 0..3 = ACGT, 4 = N. */
+WD_API int wd_dup_pairs_seqs(wd_ctx *ctx, int32_t *rows /* cap x 4 */, uint8_t *codes /* cap x 2 x seq_len */,
+                      size_t cap, uint64_t *n_rows);
+/* Measurement hook (bench.py roofline): runs the fused kernel of wd_count on the same
+ * arguments in a build that records every plane read, and returns per tile and compared
+ * position the number of distinct 32-byte sectors (and distinct 128-byte lines) of that
+ * position's plane the kernel asked for -- with its early exits, i.e. what the algorithm
+ * needs, not what a full read would move.  <= 64 compared symbols, <= 5 levels. */
+WD_API int wd_count_trace_sectors(wd_ctx *ctx, int first_slot, int n_tiles, const int32_t *plane_order, int seq_len,
+                           int edit_distance, int hamming, uint32_t *sectors /* n_tiles x seq_len */,
+                           uint32_t *lines /* n_tiles x seq_len */);
 
 /* ---- multi-GPU ------------------------------------------------------------------
+ * One process per GPU, tiles sharded over the ranks; the counter rows are combined by
+ * ONE ncclAllReduce(int64, sum) over NVLink.  Replaces one process per lane plus the
+ * "tail" concatenation of Snakefile.count_dups:146-160.
  * K7: place this rank's tile counters into a zero-initialised
  * [n_rows_total][1+5*levels] int64 device array (tile_row[i] = global row of
- * local tile i, lane_row[i] = row that accumulates its lane total) ready for one
- * ncclAllReduce(int64, sum) issued by the host through torch.distributed.
- * Replaces the cross-process "tail" concatenation of Snakefile.count_dups:146-151. */
+ * local tile i, lane_row[i] = row that accumulates its lane total), ready for
+ * wd_allreduce_i64 (or any other all-reduce on *devptr). */
 WD_API int wd_publish_counters(wd_ctx *ctx, const int32_t *tile_row, const int32_t *lane_row,
                         int n_tiles, int n_rows_total, void **devptr, size_t *n_int64);
+/* Same, into the array of the previous wd_publish_counters (not zeroed again): a rank that counts its
+ * tiles in several batches publishes each batch, then reduces once. */
+WD_API int wd_publish_add(wd_ctx *ctx, const int32_t *tile_row, const int32_t *lane_row,
+                   int n_tiles, int n_rows_total, void **devptr, size_t *n_int64);
 WD_API int wd_counters_devptr(wd_ctx *ctx, void **devptr, size_t *n_int64);
+/* NCCL communicator of this context (the library loads libnccl.so.2 on first use; no torch).
+ * Rank 0 calls wd_comm_unique_id and hands the 128 bytes to the other ranks by any means
+ * (a file, MPI, torch.distributed's store); every rank then calls wd_comm_init. */
+#define WD_COMM_ID_BYTES 128
+WD_API int wd_comm_unique_id(void *id128);
+WD_API int wd_comm_init(wd_ctx *ctx, const void *id128, int rank, int nranks);
+WD_API int wd_comm_destroy(wd_ctx *ctx);
+/* In-place sum over all ranks of n int64 at device pointer buf, enqueued on the context's stream.
+ * buf == NULL: the array of the last wd_publish_counters -- reduced on a communication stream of the
+ * library's own, behind the kernel that filled it, so that the next wd_count (whose rows go to a
+ * second array) runs while the collective is in flight. */
+WD_API int wd_allreduce_i64(wd_ctx *ctx, void *buf, size_t n);
+/* Make the context's stream wait for the all-reduces issued so far (before timing or reusing results). */
+WD_API int wd_comm_join(wd_ctx *ctx);
+/* The (all-reduced) rows of the last wd_publish_counters, copied to the host (synchronises). */
+WD_API int wd_published_fetch(wd_ctx *ctx, int64_t *rows /* n_int64 */, size_t n_int64);
 
 /* ---- exhaustive mode ---------------------------------------------------------------
  * Every well of the tile is a target out to `levels` rings (BASELINE config 3):

@@ -99,6 +99,13 @@ def levenshtein(a, b):
     return lib().orc_levenshtein(_p(a), a.size, _p(b), b.size)
 
 
+def prefix_band_min(a, b, p, k):
+    """Definition of the fused kernel's prefix test (not a reference function; welldup_oracle.c)."""
+    a = np.ascontiguousarray(a, np.uint8)
+    b = np.ascontiguousarray(b, np.uint8)
+    return lib().orc_prefix_band_min(_p(a), a.size, _p(b), int(p), int(k))
+
+
 def count_tile(planes, kinds, filt, centres, level_offsets, idx, levels, edit_distance=2, use_hamming=False,
                want_per_target=True):
     """planes: one array per compared position (repeat a plane to repeat a cycle)."""

@@ -121,6 +121,35 @@ int orc_levenshtein(const uint8_t *a, int la, const uint8_t *b, int lb) {
     return r;
 }
 
+/* Not a reference function: the definition of the exact prefix test the fused CUDA kernel stops reading a ring
+ * well with (wd_seq.cuh, PrefixDP), restated on the full edit matrix so that tests can replay which plane bytes
+ * the kernel needs.  After p symbols of b, against a of length la:
+ *   min over |j - p| <= k, 0 <= j <= la of  D[j][p] + |j - p|,   D[j][p] = edit distance(a[0..j), b[0..p)).
+ * A value > e proves Levenshtein(a, b) > e for equal-length strings and k = e / 2. */
+int orc_prefix_band_min(const uint8_t *a, int la, const uint8_t *b, int p, int k) {
+    int *col = (int *)malloc((size_t)(la + 1) * sizeof(int));
+    for (int j = 0; j <= la; ++j) col[j] = j;                    /* D[j][0] */
+    for (int c = 1; c <= p; ++c) {
+        int diag = col[0];
+        col[0] = c;
+        for (int j = 1; j <= la; ++j) {
+            const int left = col[j];
+            int v = diag + (a[j - 1] != b[c - 1]);
+            if (left + 1 < v) v = left + 1;
+            if (col[j - 1] + 1 < v) v = col[j - 1] + 1;
+            diag = left;
+            col[j] = v;
+        }
+    }
+    int best = 1 << 30;
+    for (int j = (p - k > 0 ? p - k : 0); j <= (p + k < la ? p + k : la); ++j) {
+        const int v = col[j] + (j > p ? j - p : p - j);
+        if (v < best) best = v;
+    }
+    free(col);
+    return best;
+}
+
 int orc_hamming(const uint8_t *a, const uint8_t *b, int n) {
     int d = 0;
     for (int i = 0; i < n; ++i) d += a[i] != b[i];

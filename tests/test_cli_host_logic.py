@@ -28,6 +28,7 @@ class OracleEngine:
     def __init__(self):
         self.slots = {}
         self.calls = []
+        self.modes = []
 
     # -- targets -----------------------------------------------------------------------------------
     def load_targets(self, centres, level_offsets, idx, levels):
@@ -77,13 +78,15 @@ class OracleEngine:
 
     # -- kernels --------------------------------------------------------------------------------------
     def count(self, first_slot, n_tiles, plane_order, edit_distance=2, hamming=False, mode=0, per_target=True):
-        pts, cnts, self.pairs = [], [], []
+        pts, cnts, self.pairs, self.pair_codes = [], [], [], []
+        self.modes.append(mode)
+        self._len = len(plane_order)
         for k in range(n_tiles):
             planes, kinds, filt = self._tile(first_slot + k, plane_order)
             pt, cnt = CP.count_tile(planes, kinds, filt, self.centres, self.offs, self.idx, self.levels, edit_distance, hamming)
             pts.append(pt)
             cnts.append(cnt)
-            if mode == 1:
+            if mode in (_lib.MODE_TWO_PASS, _lib.MODE_FUSED_LOG):
                 wells = np.unique(np.concatenate([self.centres, self.idx]))
                 codes, _ = CP.get_codes(planes, kinds, filt, wells.astype(np.int64))
                 row = {int(w): codes[i] for i, w in enumerate(wells)}
@@ -97,6 +100,7 @@ class OracleEngine:
                             d = int((a != b).sum()) if hamming else CP.levenshtein(a, b)
                             if d <= edit_distance:
                                 self.pairs.append((k, t, int(w), d))
+                                self.pair_codes.append(np.stack([a, b]))
         return np.array(pts), np.array(cnts)
 
     def count_async(self, first_slot, n_tiles, plane_order, edit_distance=2, hamming=False, mode=0, want_per_target=False):
@@ -105,8 +109,11 @@ class OracleEngine:
     def count_fetch(self):
         return self._pending
 
-    def dup_pairs(self):
-        return np.array(self.pairs, np.int32).reshape(-1, 4)
+    def dup_pairs(self, with_seqs=False):
+        rows = np.array(self.pairs, np.int32).reshape(-1, 4)
+        if not with_seqs:
+            return rows
+        return rows, np.array(self.pair_codes, np.uint8).reshape(len(self.pairs), 2, self._len)
 
     def get_seqs(self, slot, indices, plane_order):
         planes, kinds, filt = self._tile(slot, plane_order)
@@ -141,12 +148,13 @@ def test_count_cli_host_side_matches_reference(case, oracle_engine):
     if case["returncode"] == 0:
         assert err.getvalue() == want_err
     quiet = "-q" in case["args"] or "--quiet" in case["args"]
-    # -q: planes stay where the inflate put them; otherwise they are copied for the two-pass kernels
-    assert set(oracle_engine.calls) == ({"map"} if quiet else {"begin"})
+    # the planes stay where the inflate put them; without -q the fused kernel also logs the duplicate pairs
+    assert set(oracle_engine.calls) == {"map"}
+    assert set(oracle_engine.modes) == ({_lib.MODE_FUSED} if quiet else {_lib.MODE_FUSED_LOG})
 
 
 def test_quiet_and_logged_runs_print_the_same_report(oracle_engine):
-    """Batched zero-copy walk (-q) and tile-by-tile walk give one report."""
+    """The walk with (-q) and without the duplicate-pair log gives one report."""
     case = [c for c in MAN["count"] if c["name"] == "two_lanes"][0] if any(c["name"] == "two_lanes" for c in MAN["count"]) else MAN["count"][0]
     base = ["-f", os.path.join(GOLDEN, case["targets"]), "-r", os.path.join(GOLDEN, case["run"])] + [a for a in case["args"] if a not in ("-q", "--quiet")]
     outs = []

@@ -349,6 +349,10 @@ def test_dup_pair_log_rows(eng, oracle):
     order, tiles, (centres, offs, idx), lane = _load_case(eng, R, case, o)
     eng.count(0, len(tiles), order, o["edit"], o["hamming"], mode=1)
     rows = eng.dup_pairs()
+    # the fused kernel logs the same pairs with the same distances, and hands out both sequences
+    eng.count(0, len(tiles), order, o["edit"], o["hamming"], mode=2)
+    rows2, codes = eng.dup_pairs(with_seqs=True)
+    assert np.array_equal(rows, rows2)
     log = []
     run = os.path.join(GOLDEN, case["run"])
     targets = R.parse_target_file(os.path.join(GOLDEN, case["targets"]), levels=o["levels"] + 1, limit=o["limit"])
@@ -360,6 +364,158 @@ def test_dup_pair_log_rows(eng, oracle):
         want += [(k, c, w, d) for c, _, w, _, d in log]
     got = [(int(r[0]), int(centres[r[1]]), int(r[2]), int(r[3])) for r in rows]
     assert got == want and len(got) > 0
+    from well_duplicates_b200.reader import codes_to_strings
+    seqs = codes_to_strings(codes.reshape(-1, len(order)))
+    k = 0
+    for ti, t in enumerate(tiles):
+        seq_objs = [R.get_seqs_run(run, lane, t, R.all_indices(targets), s, e) for s, e in o["ranges"]]
+        log = []
+        R.count_tile(targets, seq_objs, o["levels"], o["edit"], o["hamming"], log)
+        for c, cseq, w, wseq, d in log:
+            assert (seqs[2 * k], seqs[2 * k + 1]) == (cseq, wseq)
+            k += 1
+    assert k == len(rows)
+
+
+@pytest.mark.parametrize("e,ham", [(2, False), (1, False), (0, False), (3, True), (5, False), (60, False), (70, True)])
+def test_fused_log_equals_two_pass_log(eng, oracle, e, ham):
+    """Distances logged by the fused kernel (read off its prefix programme) against the two-pass
+    kernel's exact_distance, incl. e >= len where every pair is a duplicate and must still be measured."""
+    from well_duplicates_b200 import synth
+    X, Y, td, centres = _synthetic_tile(11, 60000, 300, 50, 400, dup_rate=0.4, shift_share=0.5, nocall_rate=0.01)
+    eng.load_locs(synth.xy_to_locs_floats(X, Y))
+    offs, idx = eng.ring_query(centres, 5)
+    eng.load_targets(centres, offs, idx, 5)
+    eng.tile_begin(0, td.n_wells, td.n_cycles)
+    eng.tile_put_filter(0, td.filt)
+    for c in range(td.n_cycles):
+        eng.tile_put_bcl(0, c, td.planes[c])
+    order = list(range(td.n_cycles))
+    pt1, c1 = eng.count(0, 1, order, e, ham, mode=1)
+    rows1 = eng.dup_pairs()
+    pt2, c2 = eng.count(0, 1, order, e, ham, mode=2)
+    rows2 = eng.dup_pairs()
+    assert np.array_equal(pt1, pt2) and np.array_equal(c1, c2)
+    assert np.array_equal(rows1, rows2) and len(rows1) == int(c1[0, 2::5].sum()) > 0
+
+
+def test_dup_log_grows_when_every_ring_well_is_a_duplicate(eng, oracle):
+    """A tile of identical reads: every ring well of every valid target is a duplicate (amplicon-like
+    libraries, large -e).  The device log starts smaller than that; wd_dup_pairs grows it and repeats the
+    count instead of failing -- the reference logs every pair (count_well_duplicates.py:258-262)."""
+    from well_duplicates_b200 import synth
+    n, row_len, ncyc, t = 250000, 500, 20, 2400
+    rng = np.random.default_rng(5)
+    X, Y = synth.hex_lattice(n, row_len)
+    centres = rng.choice(n, size=t, replace=False).astype(np.uint32)
+    planes = np.repeat(rng.integers(1, 4, size=(ncyc, 1), dtype=np.uint8) | 0x40, n, axis=1)
+    filt = np.ones(n, np.uint8)
+    eng.load_locs(synth.xy_to_locs_floats(X, Y))
+    offs, idx = eng.ring_query(centres, 5)
+    eng.load_targets(centres, offs, idx, 5)
+    eng.tile_begin(0, n, ncyc)
+    eng.tile_put_filter(0, filt)
+    for c in range(ncyc):
+        eng.tile_put_bcl(0, c, planes[c])
+    for mode in (2, 1):
+        pt, cnt = eng.count(0, 1, list(range(ncyc)), 2, False, mode=mode)
+        rows = eng.dup_pairs()
+        assert len(rows) == idx.size > 65536 + (idx.size + t) // 8       # more than the log's first size
+        assert np.array_equal(rows[:, 2], idx) and not rows[:, 3].any() and not rows[:, 0].any()
+        assert np.array_equal(rows[:, 1], np.repeat(np.arange(t), np.diff(offs[::5].astype(np.int64))))
+        assert np.array_equal(cnt[0, 1::5], cnt[0, 2::5])                # Wells == Dups at every level
+
+
+def test_empty_ring_is_reported_only_for_valid_centres(eng):
+    """count_well_duplicates.py:249 asserts a ring holds wells when it gets to it -- i.e. for a target whose
+    centre passes the filter of the tile being counted; a list with an empty ring on a never-valid centre runs."""
+    eng.load_targets([5, 9], [0, 2, 2, 3, 4], [1, 2, 8, 10], 2)          # target 0: ring 2 empty
+    eng.tile_begin(0, 100, 1)
+    filt = np.ones(100, np.uint8)
+    filt[5] = 0
+    eng.tile_put_filter(0, filt)
+    eng.tile_put_bcl(0, 0, np.full(100, 5, np.uint8))
+    for mode in (0, 1, 2):
+        pt, cnt = eng.count(0, 1, [0], 2, False, mode=mode)
+        assert cnt[0, 0] == 1 and pt[0, 0, 0] == 0 and pt[0, 1].tolist() == [1, 1, 1, 1, 1]
+    filt[5] = 1
+    eng.tile_put_filter(0, filt)
+    for mode in (0, 1, 2):
+        with pytest.raises(AssertionError):
+            eng.count(0, 1, [0], 2, False, mode=mode)
+
+
+def test_publish_counters_rows(eng, oracle):
+    """K7 (wd_publish_counters): every tile row lands where the map says, lane rows hold the sums of their
+    tiles, every other row stays zero; the single-rank all-reduce leaves the buffer as it is."""
+    R, CP = oracle
+    case = [c for c in MAN["count"] if c["name"] == "lev_default"][0]
+    o = parse_count_args(case["args"])
+    order, tiles, _, lane = _load_case(eng, R, case, o)
+    _, cnt = eng.count(0, len(tiles), order, o["edit"], o["hamming"], mode=0, per_target=False)
+    n_rows = 11
+    tile_row = np.array([7, 2][:len(tiles)], np.int32)
+    lane_row = np.array([9, 10][:len(tiles)], np.int32)
+    ptr, n = eng.publish_counters(tile_row, lane_row, n_rows)
+    assert n == n_rows * cnt.shape[1]
+    eng.allreduce_published()
+    buf = eng.published_fetch(n).reshape(n_rows, -1)
+    want = np.zeros_like(buf)
+    for k in range(len(tiles)):
+        want[tile_row[k]] = cnt[k]
+        want[lane_row[k]] += cnt[k]
+    assert np.array_equal(buf, want) and buf.any()
+    # both tiles into one lane row
+    ptr, n = eng.publish_counters(tile_row, np.full(len(tiles), 4, np.int32), n_rows)
+    buf = eng.published_fetch(n).reshape(n_rows, -1)
+    assert np.array_equal(buf[4], cnt.sum(axis=0))
+
+
+def test_sector_trace_equals_a_host_replay(eng, oracle):
+    """wd_count_trace_sectors (bench.py's roofline numerator): with the schedule pinned to one cycle per round,
+    the sectors the fused kernel reads at position p are those of the centres (as far as the programme looks
+    ahead) and of the ring wells whose first p symbols have not yet proved dist > e -- replayed with the oracle."""
+    R, CP = oracle
+    from well_duplicates_b200 import synth
+    X, Y, td, centres = _synthetic_tile(3, 40000, 250, 24, 200, dup_rate=0.3, shift_share=0.4)
+    eng.load_locs(synth.xy_to_locs_floats(X, Y))
+    offs, idx = eng.ring_query(centres, 5)
+    eng.load_targets(centres, offs, idx, 5)
+    eng.tile_begin(0, td.n_wells, td.n_cycles)
+    eng.tile_put_filter(0, td.filt)
+    for c in range(td.n_cycles):
+        eng.tile_put_bcl(0, c, td.planes[c])
+    order = list(range(td.n_cycles))
+    e, k, L = 2, 1, td.n_cycles
+    eng.set_tuning(step0=1, step1=1, centre_chunk=8)
+    try:
+        sectors, lines = eng.trace_sectors(0, 1, order, e, False)
+    finally:
+        eng.set_tuning()
+    codes, _ = CP.get_codes([td.planes[c] for c in order], ["bcl"] * L, td.filt, np.arange(td.n_wells, dtype=np.int64))
+    need = [set() for _ in range(L)]
+    for t, c in enumerate(centres):
+        if not td.filt[c] & 1:
+            continue
+        ring = idx[offs[5 * t]:offs[5 * t + 5]]
+        deepest = 0
+        for w in ring:
+            p = 0                                    # symbols of w read before its prefix proves dist > e
+            while p < L:
+                p += 1
+                if CP.prefix_band_min(codes[c], codes[w], p, k) > e:
+                    break
+            for q in range(p):
+                need[q].add(int(w) >> 5)
+            deepest = max(deepest, p)
+        # the centre is decoded 8 cycles at a time, as far as the deepest round looked ahead (p + k)
+        known = 0
+        while known < min(L, deepest + k):
+            known = min(L, known + 8)
+        for q in range(known):
+            need[q].add(int(c) >> 5)
+    assert sectors[0].tolist() == [len(s) for s in need]
+    assert (lines[0] <= sectors[0]).all() and (4 * lines[0] >= sectors[0]).all()
 
 
 def test_error_paths(eng):
@@ -367,8 +523,6 @@ def test_error_paths(eng):
         eng.count(0, 1, [0] * 2000, 2, False)                 # longer than WD_MAX_SEQ_LEN
     with pytest.raises(ValueError):
         eng.count(50000, 1, [0], 2, False)                    # slot never begun
-    with pytest.raises(AssertionError):
-        eng.load_targets([5], [0, 2, 2], [1, 2], 2)           # empty ring, count_well_duplicates.py:249
     eng.load_targets([5], [0, 2], [1, 200], 1)
     eng.tile_begin(0, 100, 1)
     eng.tile_put_filter(0, np.ones(100, np.uint8))

@@ -160,7 +160,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), name
-    assert _lib.load().wd_abi_version() == 1
+    assert _lib.load().wd_abi_version() == _lib.ABI_VERSION == 2
 
 
 def test_no_cpu_fallback_without_a_gpu():

@@ -15,6 +15,15 @@ WD_E_NOENT, WD_E_IO, WD_E_EOF, WD_E_DATA = -7, -8, -9, -10
 PLANE_EMPTY, PLANE_BCL, PLANE_CBCL, PLANE_CBCL_EXCL = 0, 1, 2, 3
 MAX_LEVELS = 15
 MAX_SEQ_LEN = 1024
+ABI_VERSION = 2
+MODE_FUSED, MODE_TWO_PASS, MODE_FUSED_LOG = 0, 1, 2
+COMM_ID_BYTES = 128
+
+
+class Tuning(C.Structure):
+    """struct wd_tuning (include/welldup.h)."""
+    _fields_ = [("step0", C.c_int32), ("step1", C.c_int32), ("centre_chunk", C.c_int32), ("head_planes", C.c_int32),
+                ("head_groups", C.c_int32), ("visit_order", C.c_int32), ("reserved", C.c_int32 * 10)]
 
 
 class CudaError(RuntimeError):
@@ -69,6 +78,16 @@ SIGNATURES = {
     "wd_count_async": (C.c_int, [_p, C.c_int, C.c_int, _p, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int]),
     "wd_count_fetch": (C.c_int, [_p, _p, _p]),
     "wd_dup_pairs": (C.c_int, [_p, _p, C.c_size_t, _u64p]),
+    "wd_dup_pairs_seqs": (C.c_int, [_p, _p, _p, C.c_size_t, _u64p]),
+    "wd_count_trace_sectors": (C.c_int, [_p, C.c_int, C.c_int, _p, C.c_int, C.c_int, C.c_int, _p, _p]),
+    "wd_set_tuning": (C.c_int, [_p, _p]),
+    "wd_comm_unique_id": (C.c_int, [_p]),
+    "wd_comm_init": (C.c_int, [_p, _p, C.c_int, C.c_int]),
+    "wd_comm_destroy": (C.c_int, [_p]),
+    "wd_allreduce_i64": (C.c_int, [_p, _p, C.c_size_t]),
+    "wd_published_fetch": (C.c_int, [_p, _p, C.c_size_t]),
+    "wd_comm_join": (C.c_int, [_p]),
+    "wd_publish_add": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, C.POINTER(_p), C.POINTER(C.c_size_t)]),
     "wd_publish_counters": (C.c_int, [_p, _p, _p, C.c_int, C.c_int, C.POINTER(_p), C.POINTER(C.c_size_t)]),
     "wd_counters_devptr": (C.c_int, [_p, C.POINTER(_p), C.POINTER(C.c_size_t)]),
     "wd_inflate_batch": (C.c_int, [C.POINTER(InflateJob), C.c_size_t, C.c_int]),
@@ -93,8 +112,8 @@ def load():
         fn = getattr(lib, name)
         fn.restype = res
         fn.argtypes = args
-    if lib.wd_abi_version() != 1:
-        raise ImportError("libwelldup.so has ABI version %d, expected 1" % lib.wd_abi_version())
+    if lib.wd_abi_version() != ABI_VERSION:
+        raise ImportError("libwelldup.so has ABI version %d, expected %d" % (lib.wd_abi_version(), ABI_VERSION))
     _lib = lib
     return lib
 

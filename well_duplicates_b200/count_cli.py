@@ -7,8 +7,10 @@ import re
 import sys
 from argparse import ArgumentDefaultsHelpFormatter, ArgumentParser
 
+import numpy as np
+
 from . import reader as bcl_direct_reader
-from .report import dupl_from_per_target, output_writer, write_report
+from .report import write_report
 from .targets import load_targets
 
 __VERSION__ = 0.3
@@ -126,20 +128,18 @@ def main(argv=None):
     eng.load_targets(centres, level_offsets, idx, args.level)
     n_unique = len(targets.get_all_indices())
     wanted = [c for s, e in cycles for c in range(s, e)]
-    # the duplicate-pair log needs the two-pass kernels and per-tile ordering on stderr
-    mode = 0 if args.quiet else 1
+    from . import _lib
     from .staging import lane_batches
     stager = bcl_direct_reader.default_stager(bcl_reader._cbcl_cache)
 
     # Files -> page-locked planes on native threads, one batch ahead of the GPU (staging.py), across
     # lane boundaries: the first tiles of the next lane inflate while this lane is finished and printed.
-    # -q: many tiles per launch, planes stay in host memory and the fused kernel pulls the sectors
-    # it needs.  Otherwise one tile at a time, in the reference's log order, planes copied to HBM
-    # for the two-pass kernels that feed the duplicate-pair log.
+    # Many tiles per launch; the planes stay in host memory and the fused kernel pulls the sectors it
+    # needs.  Without -q the same kernel also logs every duplicate pair (count_well_duplicates.py:258-262)
+    # and the log is printed tile by tile, in the reference's order, once the batch has been counted.
     lanes = [str(lane) for lane in lanes]
     walk = ["%s/%s" % (lane, t) for lane in lanes for t in tiles]
-    lane_dupl = {lane: {} for lane in lanes}      # per-target lists (log mode), as the reference builds them
-    lane_rows = {lane: {} for lane in lanes}      # counter rows of the device reduction (-q)
+    lane_rows = {lane: {} for lane in lanes}      # counter rows of the device reduction
     todo = {lane: len(tiles) for lane in lanes}
 
     def open_tile(name):
@@ -151,48 +151,47 @@ def main(argv=None):
         say("Reading tile %s in lane %s" % (t, lane))
 
     def finish(lane):
-        if not args.quiet:
-            output_writer(lane, len(targets), lane_dupl[lane], verbose=not args.summary_only)
-            return
         names = sorted(lane_rows[lane])
         # output_writer infers the level count from the first tile with a valid target: none -> no level lines
         levels = args.level if any(int(lane_rows[lane][t][0]) for t in names) else 0
         write_report(sys.stdout, lane, len(targets), names, [lane_rows[lane][t][:1 + 5 * levels] for t in names], levels,
                      verbose=not args.summary_only)
 
-    for names, staged in lane_batches(stager, open_tile, walk, wanted, per_batch=None if args.quiet else 1,
-                                      announce=announce):
-        plane_of = stager.deliver(eng, staged, first_slot=0, zero_copy=args.quiet)
+    mode = _lib.MODE_FUSED if args.quiet else _lib.MODE_FUSED_LOG
+    for names, staged in lane_batches(stager, open_tile, walk, wanted, on_error=announce):
+        plane_of = stager.deliver(eng, staged, first_slot=0, zero_copy=True)
         order = [plane_of[c] for c in wanted]
-        say("Got %i sequences from %i contiguous cycle ranges." % (n_unique * len(cycles), len(cycles)))
-        if args.quiet:
-            # nothing to log: the counter rows of the device reduction are the report (report.write_report)
-            _, counters = eng.count(0, len(names), order, args.edit_distance, args.hamming, mode=0, per_target=False)
-        else:
-            per_target, _ = eng.count(0, len(names), order, args.edit_distance, args.hamming, mode=mode, per_target=True)
-            pairs = eng.dup_pairs()
+        try:
+            _, counters = eng.count(0, len(names), order, args.edit_distance, args.hamming, mode=mode, per_target=False)
+        except IndexError:
+            announce(names[0])         # a well beyond the tile: the reference fails on the first tile of this size
+            raise
+        pairs, codes = (None, None) if args.quiet else eng.dup_pairs(with_seqs=True)
+        first = {}
+        if pairs is not None and len(pairs):
+            seqs = bcl_direct_reader.codes_to_strings(codes.reshape(-1, len(order)))
+            with_rows, at = np.unique(pairs[:, 0], return_index=True)       # rows are sorted by tile
+            first = dict(zip(with_rows.tolist(), at.tolist()))
         for k, name in enumerate(names):
             lane, tname = name.split("/")
-            if args.quiet:
-                lane_rows[lane][tname] = counters[k]
-            else:
-                lane_dupl[lane][tname] = dupl_from_per_target(per_target[k], args.level)
-                rows = [r for r in pairs if r[0] == k]
-                if rows:
-                    wells = sorted({int(centres[r[1]]) for r in rows} | {int(r[2]) for r in rows})
-                    codes, _ = eng.get_seqs(k, wells, order)
-                    seq = dict(zip(wells, bcl_direct_reader.codes_to_strings(codes)))
-                    for _, t_ord, well, dist in rows:
-                        c = int(centres[t_ord])
-                        say("center seq at {:>07}: {}".format(c, seq[c]))
-                        say("well seq at   {:>07}: {}".format(int(well), seq[int(well)]))
-                        say("edit distance: {}".format(int(dist)))
+            announce(name)
+            say("Got %i sequences from %i contiguous cycle ranges." % (n_unique * len(cycles), len(cycles)))
+            if k in first:
+                i = first[k]
+                while i < len(pairs) and pairs[i, 0] == k:
+                    _, t_ord, well, dist = pairs[i].tolist()
+                    say("center seq at {:>07}: {}".format(int(centres[t_ord]), seqs[2 * i]))
+                    say("well seq at   {:>07}: {}".format(well, seqs[2 * i + 1]))
+                    say("edit distance: {}".format(dist))
+                    i += 1
+            lane_rows[lane][tname] = counters[k]
             todo[lane] -= 1
             if todo[lane] == 0:
                 finish(lane)
     if not tiles:
         for lane in lanes:
             finish(lane)
+
 
 if __name__ == "__main__":
     main()

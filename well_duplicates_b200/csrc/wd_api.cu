@@ -92,9 +92,9 @@ int wd_create(int device, wd_ctx **out) {
         delete ctx;
         WD_FAIL(WD_E_CUDA, "cudaStreamCreate failed: %s", cudaGetErrorString(e));
     }
-    // scattered 1-byte gathers: do not let L2 pull whole 64/128-byte lines from HBM (a hint; failure is harmless)
-    const char *g = getenv("WELLDUP_L2_FETCH");
-    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, g ? (size_t)atoi(g) : 32);
+    // scattered 1-byte gathers: ask L2 not to pull whole lines from HBM (a hint this part ignores -- the plane
+    // loads carry their own fill size, wd_kernels23.cuh: ld_plane_u8; failure is harmless)
+    cudaDeviceSetLimit(cudaLimitMaxL2FetchGranularity, 32);
     cudaGetLastError();
     *out = ctx;
     return WD_OK;
@@ -111,22 +111,45 @@ int wd_set_l2_fetch_granularity(wd_ctx *ctx, int bytes, int *previous) {
     return WD_OK;
 }
 
+int wd_set_tuning(wd_ctx *ctx, const wd_tuning *t) {
+    if (ctx == nullptr) WD_FAIL(WD_E_ARG, "wd_set_tuning: null context");
+    Tuning tu;
+    if (t != nullptr) {
+        if (t->step0 < 0 || t->step0 > 8 || t->step1 < 0 || t->step1 > 8) WD_FAIL(WD_E_ARG, "wd_set_tuning: rounds read 1..8 cycles (0 = default)");
+        if (t->centre_chunk != 0 && t->centre_chunk != 8 && t->centre_chunk != 16 && t->centre_chunk != 32)
+            WD_FAIL(WD_E_ARG, "wd_set_tuning: centre_chunk is 8, 16 or 32 (0 = default)");
+        if (t->head_planes > 8) WD_FAIL(WD_E_ARG, "wd_set_tuning: at most 8 head planes");
+        tu.step0 = t->step0;
+        tu.step1 = t->step1;
+        tu.centre_chunk = t->centre_chunk;
+        tu.head_planes = t->head_planes;
+        tu.head_groups = t->head_groups;
+        tu.visit_order = t->visit_order;
+    }
+    ctx->tuning = tu;
+    return WD_OK;
+}
+
 int wd_destroy(wd_ctx *ctx) {
     if (ctx == nullptr) return WD_OK;
     cudaSetDevice(ctx->device);
     cudaDeviceSynchronize();
+    comm_destroy(ctx);
     DevBuf *bufs[] = {&ctx->xy, &ctx->px, &ctx->py, &ctx->bbox, &ctx->cell_start, &ctx->cell_cursor, &ctx->cell_wells,
                       &ctx->scan_tmp, &ctx->q_centres, &ctx->q_counts, &ctx->q_offsets, &ctx->q_idx, &ctx->q_tmp,
                       &ctx->q_flag, &ctx->descs, &ctx->order_dev, &ctx->packed, &ctx->per_target, &ctx->counters,
                       &ctx->publish, &ctx->dup_rows, &ctx->dup_count, &ctx->gs_idx, &ctx->gs_packed, &ctx->gs_codes,
                       &ctx->targets.tgt_off, &ctx->targets.slot_well, &ctx->targets.slot_level, &ctx->targets.slot_csr,
-                      &ctx->targets.level_len, &ctx->targets.visit, &ctx->x_packed, &ctx->x_counts, &ctx->x_pre, &ctx->x_ringlen, &ctx->x_flags, &ctx->x_tally, &ctx->x_work};
+                      &ctx->targets.level_len, &ctx->targets.visit, &ctx->head, &ctx->trace, &ctx->trace_counts, &ctx->dup_codes, &ctx->excl_totals, &ctx->x_packed, &ctx->x_counts, &ctx->x_pre, &ctx->x_ringlen, &ctx->x_flags, &ctx->x_tally, &ctx->x_work};
     for (DevBuf *b : bufs) b->release();
     for (TileSlot &s : ctx->slots) {
         s.planes.release(); s.filter.release(); s.pfmask.release(); s.pfrank.release();
-        s.kind_dev.release(); s.pfcount_dev.release(); s.head.release();
+        s.kind_dev.release(); s.pfcount_dev.release();
     }
     for (cudaEvent_t ev : ctx->copy_events) cudaEventDestroy(ev);
+    if (ctx->pub_ready) cudaEventDestroy(ctx->pub_ready);
+    for (cudaEvent_t ev : ctx->comm_done) if (ev) cudaEventDestroy(ev);
+    if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
     if (ctx->copy_stream) cudaStreamDestroy(ctx->copy_stream);
     if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
     delete ctx;
@@ -217,6 +240,7 @@ int wd_targets_load(wd_ctx *ctx, const uint32_t *centres, const uint32_t *level_
     std::vector<std::pair<uint32_t, uint32_t>> tmp;   // (well, csr position)
     uint32_t max_well = 0;
     uint32_t pos = 0;
+    bool has_empty = false;
     for (uint32_t i = 0; i < t; ++i) {
         tgt_off[i] = pos;
         slot_well[pos] = centres[i];
@@ -230,8 +254,9 @@ int wd_targets_load(wd_ctx *ctx, const uint32_t *centres, const uint32_t *level_
         for (int l = 0; l < levels; ++l) {
             const uint32_t s = level_offsets[(size_t)i * levels + l], e = level_offsets[(size_t)i * levels + l + 1];
             if (e < s) WD_FAIL(WD_E_ARG, "wd_targets_load: level_offsets must be non-decreasing");
-            // count_well_duplicates.py:249 asserts every ring holds at least one well
-            if (e == s) WD_FAIL(WD_E_ASSERT, "target %u (centre %u) has no wells at level %d", i, centres[i], l + 1);
+            // count_well_duplicates.py:249 asserts that every ring holds a well -- when it gets to the target, i.e.
+            // in a tile where the centre passes the filter: the kernels report that (wd_count_fetch)
+            if (e == s) has_empty = true;
             level_len[(size_t)i * levels + l] = e - s;
         }
         for (uint32_t k = a; k < b; ++k) tmp.emplace_back(idx[k], k);
@@ -275,6 +300,8 @@ int wd_targets_load(wd_ctx *ctx, const uint32_t *centres, const uint32_t *level_
     tl.n_slots = n_slots;
     tl.max_well = max_well;
     tl.h_idx.assign(idx, idx + n_ring);
+    tl.h_slot_csr.swap(slot_csr);
+    tl.has_empty_ring = has_empty;
     return WD_OK;
 }
 
@@ -453,29 +480,33 @@ int wd_count_fetch(wd_ctx *ctx, int32_t *per_target, int64_t *tile_counters) {
     WD_CUDA(cudaSetDevice(ctx->device));
     cudaStream_t st = ctx->stream;
     const size_t width = 1 + 5 * (size_t)ctx->last_levels;
-    if (tile_counters)
-        WD_CUDA(cudaMemcpyAsync(tile_counters, ctx->counters.p, (size_t)ctx->last_tiles * width * 8, cudaMemcpyDeviceToHost, st));
+    const size_t n_cnt = (size_t)ctx->last_tiles * width;
+    if (tile_counters) WD_CUDA(cudaMemcpyAsync(tile_counters, ctx->counters.p, n_cnt * 8, cudaMemcpyDeviceToHost, st));
     if (per_target) {
         if (!ctx->last_per_target) WD_FAIL(WD_E_ARG, "wd_count_fetch: the count was issued without per-target output");
         WD_CUDA(cudaMemcpyAsync(per_target, ctx->per_target.p,
                                 (size_t)ctx->last_tiles * ctx->last_t * (1 + 2 * (size_t)ctx->last_levels) * 4,
                                 cudaMemcpyDeviceToHost, st));
     }
-    // excluded CBCL blocks must hold exactly the PF wells (cbcl_read.py:130-131)
-    std::vector<uint32_t> pf((size_t)ctx->last_tiles, 0);
-    for (int k = 0; k < ctx->last_tiles; ++k) {
-        TileSlot &s = ctx->slots[ctx->last_first_slot + k];
-        if (s.has_excl && s.rank_valid)
-            WD_CUDA(cudaMemcpyAsync(&pf[k], s.pfrank.as<uint32_t>() + (s.n + 63) / 64, 4, cudaMemcpyDeviceToHost, st));
-    }
+    // two status words behind the counter rows, written by the counting kernels
+    unsigned long long status[2] = {0, 0};
+    WD_CUDA(cudaMemcpyAsync(status, ctx->counters.as<unsigned long long>() + n_cnt, 16, cudaMemcpyDeviceToHost, st));
     WD_CUDA(cudaStreamSynchronize(st));
-    for (int k = 0; k < ctx->last_tiles; ++k) {
+    if (status[1] != 0) {
+        // excluded CBCL blocks must hold exactly the PF wells (cbcl_read.py:130-131)
+        const int k = (int)(uint32_t)~status[1];
         TileSlot &s = ctx->slots[ctx->last_first_slot + k];
-        if (!(s.has_excl && s.rank_valid)) continue;
+        uint32_t pf = 0;
+        WD_CUDA(cudaMemcpy(&pf, s.pfrank.as<uint32_t>() + (s.n + 63) / 64, 4, cudaMemcpyDeviceToHost));
         for (int p = 0; p < s.n_planes; ++p)
-            if (s.kind[p] == WD_PLANE_CBCL_EXCL && s.n_block[p] != pf[k])
+            if (s.kind[p] == WD_PLANE_CBCL_EXCL && s.n_block[p] != pf)
                 WD_FAIL(WD_E_ASSERT, "tile slot %d plane %d: excluded CBCL block holds %u clusters but %u wells pass the filter",
-                        ctx->last_first_slot + k, p, s.n_block[p], pf[k]);
+                        ctx->last_first_slot + k, p, s.n_block[p], pf);
+    }
+    if (status[0] != 0) {
+        const unsigned long long v = ~status[0];
+        WD_FAIL(WD_E_ASSERT, "target %u has a ring without wells (its centre passes the filter of tile %u of the batch)",
+                (uint32_t)v, (uint32_t)(v >> 32));
     }
     return WD_OK;
 }
@@ -487,50 +518,78 @@ int wd_count(wd_ctx *ctx, int first_slot, int n_tiles, const int32_t *plane_orde
     return wd_count_fetch(ctx, per_target, tile_counters);
 }
 
-int wd_dup_pairs(wd_ctx *ctx, int32_t *rows, size_t cap, uint64_t *n_rows) {
-    if (ctx == nullptr || n_rows == nullptr) WD_FAIL(WD_E_ARG, "wd_dup_pairs: null argument");
-    if (ctx->dup_cap == 0) WD_FAIL(WD_E_ARG, "wd_dup_pairs: the last count was not run in two-pass mode (mode 1)");
+int wd_count_trace_sectors(wd_ctx *ctx, int first_slot, int n_tiles, const int32_t *plane_order, int seq_len,
+                           int edit_distance, int hamming, uint32_t *sectors, uint32_t *lines) {
+    if (ctx == nullptr || plane_order == nullptr || sectors == nullptr || lines == nullptr)
+        WD_FAIL(WD_E_ARG, "wd_count_trace_sectors: null argument");
     WD_CUDA(cudaSetDevice(ctx->device));
-    cudaStream_t st = ctx->stream;
-    unsigned long long n = 0;
-    WD_CUDA(cudaMemcpyAsync(&n, ctx->dup_count.p, 8, cudaMemcpyDeviceToHost, st));
-    WD_CUDA(cudaStreamSynchronize(st));
-    *n_rows = n;
-    if (n > ctx->dup_cap) WD_FAIL(WD_E_CAPACITY, "duplicate-pair log overflowed (%llu pairs, room for %zu)", n, ctx->dup_cap);
-    if (n > cap || rows == nullptr) {
-        if (n == 0) return WD_OK;
-        WD_FAIL(WD_E_CAPACITY, "wd_dup_pairs: %llu rows needed, caller provided %zu", n, cap);
-    }
-    std::vector<int32_t> h((size_t)n * 4);
-    WD_CUDA(cudaMemcpyAsync(h.data(), ctx->dup_rows.p, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
-    WD_CUDA(cudaStreamSynchronize(st));
-    // reference log order: tile, then target / level / well in file order == CSR position
-    std::vector<size_t> ord((size_t)n);
+    return count_trace(ctx, first_slot, n_tiles, plane_order, seq_len, edit_distance, hamming, sectors, lines);
+}
+
+// reference log order: tile, then target / level / well in file order == position in the caller's list
+static int dup_pairs_sorted(wd_ctx *ctx, std::vector<int32_t> &raw, std::vector<size_t> &ord) {
+    if (ctx->dup_cap == 0 || ctx->last_tiles == 0)
+        WD_FAIL(WD_E_ARG, "wd_dup_pairs: the last count did not log duplicate pairs (mode 1 or 2)");
+    WD_CUDA(cudaSetDevice(ctx->device));
+    WD_TRY(dup_rows_fetch(ctx, raw));
+    const size_t n = raw.size() / 4;
+    const std::vector<uint32_t> &csr = ctx->targets.h_slot_csr;
+    ord.resize(n);
     for (size_t i = 0; i < n; ++i) ord[i] = i;
     std::sort(ord.begin(), ord.end(), [&](size_t a, size_t b) {
-        if (h[a * 4] != h[b * 4]) return h[a * 4] < h[b * 4];
-        return (uint32_t)h[a * 4 + 2] < (uint32_t)h[b * 4 + 2];
+        if (raw[a * 4] != raw[b * 4]) return raw[a * 4] < raw[b * 4];
+        return csr[(uint32_t)raw[a * 4 + 2]] < csr[(uint32_t)raw[b * 4 + 2]];
     });
+    return WD_OK;
+}
+
+int wd_dup_pairs_seqs(wd_ctx *ctx, int32_t *rows, uint8_t *codes, size_t cap, uint64_t *n_rows) {
+    if (ctx == nullptr || n_rows == nullptr) WD_FAIL(WD_E_ARG, "wd_dup_pairs: null argument");
+    std::vector<int32_t> raw;
+    std::vector<size_t> ord;
+    WD_TRY(dup_pairs_sorted(ctx, raw, ord));
+    const size_t n = ord.size();
+    *n_rows = n;
+    if (n == 0) return WD_OK;
+    if (n > cap || rows == nullptr) WD_FAIL(WD_E_CAPACITY, "wd_dup_pairs: %zu rows needed, caller provided %zu", n, cap);
+    std::vector<uint8_t> h_codes;
+    if (codes != nullptr) WD_TRY(dup_seqs(ctx, raw, h_codes));
+    const size_t len2 = 2 * (size_t)ctx->last_seq_len;
     for (size_t i = 0; i < n; ++i) {
-        const int32_t *r = &h[ord[i] * 4];
+        const int32_t *r = &raw[ord[i] * 4];
         rows[i * 4 + 0] = r[0];
         rows[i * 4 + 1] = r[1];
-        rows[i * 4 + 2] = (int32_t)ctx->targets.h_idx[(uint32_t)r[2]];
+        rows[i * 4 + 2] = (int32_t)ctx->targets.h_idx[ctx->targets.h_slot_csr[(uint32_t)r[2]]];
         rows[i * 4 + 3] = r[3];
+        if (codes != nullptr) memcpy(codes + i * len2, h_codes.data() + ord[i] * len2, len2);
     }
     return WD_OK;
 }
 
+int wd_dup_pairs(wd_ctx *ctx, int32_t *rows, size_t cap, uint64_t *n_rows) {
+    return wd_dup_pairs_seqs(ctx, rows, nullptr, cap, n_rows);
+}
+
 // ---- multi-GPU -----------------------------------------------------------------------------------
-int wd_publish_counters(wd_ctx *ctx, const int32_t *tile_row, const int32_t *lane_row, int n_tiles, int n_rows_total,
-                        void **devptr, size_t *n_int64) {
+static int publish_any(wd_ctx *ctx, const int32_t *tile_row, const int32_t *lane_row, int n_tiles, int n_rows_total,
+                       void **devptr, size_t *n_int64, bool keep) {
     if (ctx == nullptr || tile_row == nullptr || lane_row == nullptr) WD_FAIL(WD_E_ARG, "wd_publish_counters: null argument");
     if (n_rows_total < 1) WD_FAIL(WD_E_ARG, "wd_publish_counters: n_rows_total must be positive");
     WD_CUDA(cudaSetDevice(ctx->device));
-    WD_TRY(publish_counters(ctx, tile_row, lane_row, n_tiles, n_rows_total));
-    if (devptr) *devptr = ctx->publish.p;
+    WD_TRY(publish_counters(ctx, tile_row, lane_row, n_tiles, n_rows_total, keep));
+    if (devptr) *devptr = ctx->publish.as<unsigned long long>() + (size_t)ctx->publish_cur * ctx->publish_n;
     if (n_int64) *n_int64 = ctx->publish_n;
     return WD_OK;
+}
+
+int wd_publish_counters(wd_ctx *ctx, const int32_t *tile_row, const int32_t *lane_row, int n_tiles, int n_rows_total,
+                        void **devptr, size_t *n_int64) {
+    return publish_any(ctx, tile_row, lane_row, n_tiles, n_rows_total, devptr, n_int64, false);
+}
+
+int wd_publish_add(wd_ctx *ctx, const int32_t *tile_row, const int32_t *lane_row, int n_tiles, int n_rows_total,
+                   void **devptr, size_t *n_int64) {
+    return publish_any(ctx, tile_row, lane_row, n_tiles, n_rows_total, devptr, n_int64, true);
 }
 
 int wd_counters_devptr(wd_ctx *ctx, void **devptr, size_t *n_int64) {

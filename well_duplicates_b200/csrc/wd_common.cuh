@@ -60,7 +60,9 @@ struct TileDesc {                 // what the kernels see (array in device memor
     const uint32_t *pfrank;       // ceil(n/64) words: #PF wells before block (K3)
     const uint8_t *kind;          // n_planes bytes: WD_PLANE_*
     uint32_t n;                   // wells on the tile
-    uint32_t flags;               // bit0: pfmask / pfrank are valid
+    uint32_t flags;               // bit0: pfmask / pfrank are valid; bit1: excl_expect is to be checked
+    uint32_t excl_expect;         // cluster count of the tile's excluded CBCL blocks: must equal the PF total (cbcl_read.py:130-131)
+    uint32_t reserved;
     // host-mapped tiles only: the planes of the first compared positions are copied to HBM by DMA
     // (head[j] = plane of position j); head_delta = head - planes (mod 2^64), so planes + head_delta
     // + j * head_stride addresses them
@@ -72,7 +74,9 @@ struct TileSlot {
     uint32_t n = 0;
     int n_planes = 0;
     size_t stride = 0;
-    DevBuf planes, filter, pfmask, pfrank, kind_dev, pfcount_dev, head;
+    DevBuf planes, filter, pfmask, pfrank, kind_dev, pfcount_dev;
+    uint8_t *head_ptr = nullptr;       // host-mapped: this tile's head planes inside ctx->head for the count being issued
+    size_t head_stride = 0;
     const uint8_t *mapped = nullptr;   // planes left in pinned host memory (wd_tile_map_host): device view of it
     const uint8_t *mapped_host = nullptr;     // ... and the host view (source of DMA copies)
     const uint8_t *mapped_filter = nullptr;   // same for the filter bytes (optional)
@@ -103,7 +107,20 @@ struct TargetList {
     DevBuf visit;        // u32 [t] targets in ascending order of their centre well: the fused kernel walks
                          //         them in this order, so that a CTA's targets sit on neighbouring rows of a
                          //         plane (few pages / DRAM rows per CTA); results are stored by target ordinal
-    std::vector<uint32_t> h_idx;   // host copy of the caller's idx[] (duplicate-pair log)
+    std::vector<uint32_t> h_idx;        // host copy of the caller's idx[] (duplicate-pair log)
+    std::vector<uint32_t> h_slot_csr;   // ... and of slot_csr: a logged slot -> position in the caller's list
+    bool has_empty_ring = false;        // some target has a ring without wells: an AssertionError of the reference
+                                        // (count_well_duplicates.py:249) -- but only once such a target's centre
+                                        // passes the filter of a tile that is counted
+};
+
+// knobs of wd_count (wd_set_tuning); 0 / negative = the library's choice
+struct Tuning {
+    int step0 = 0, step1 = 0;      // cycles read per round of the fused kernel (first, later), 1..8
+    int centre_chunk = 0;          // centre cycles decoded per warp-wide load: 8, 16 or 32
+    int head_planes = -1;          // host-mapped tiles: compared positions whose planes go to HBM by DMA, 0..8
+    int head_groups = 0;           // ... in how many tile groups, pipelined against the counting kernels
+    int visit_order = -1;          // 0: targets in list order, 1 / -1: in ascending order of their centre well
 };
 
 }  // namespace wd
@@ -145,8 +162,27 @@ struct wd_ctx {
     std::vector<unsigned long long> order_off;   // plane order / kinds / tile descriptors as last uploaded
     std::vector<uint8_t> order_kind, descs_host;
     std::vector<int32_t> publish_map;   // tile_row ++ lane_row as last uploaded behind the publish buffer
-    size_t dup_cap = 0;
+    size_t dup_cap = 0;               // rows the duplicate-pair log of the last count has room for (0: not logged)
+    size_t dup_cap_wanted = 0;        // ... and what a repeat of it after an overflow asks for
+    std::vector<int32_t> dup_raw;     // rows of the last logged count once fetched (wd_dup_pairs is called twice: size, rows)
+    bool dup_raw_valid = false;
     uint64_t last_h2d_bytes = 0;      // bytes the last wd_count copied to HBM itself (head planes of host-mapped tiles)
+    wd::Tuning tuning;
+    // arguments of the last count, kept so that wd_dup_pairs can grow the log and run it again
+    std::vector<int32_t> last_order;
+    int last_e = 0, last_hamming = 0, last_mode = 0, last_seq_len = 0;
+    bool last_all_bcl = true;
+    wd::DevBuf head;                  // host-mapped tiles: [tile][head plane][head stride] of the last count
+    wd::DevBuf trace, trace_counts;   // wd_count_trace_sectors
+    wd::DevBuf dup_codes;             // wd_dup_pairs_seqs
+    wd::DevBuf excl_totals;           // wd_count_fetch: PF totals of the tiles with excluded CBCL blocks
+    // multi-GPU (wd_comm.cc)
+    void *comm = nullptr;             // ncclComm_t
+    int comm_rank = 0, comm_ranks = 1;
+    cudaStream_t comm_stream = nullptr;          // the all-reduce of one step runs under the kernels of the next
+    cudaEvent_t pub_ready = nullptr, comm_done[2] = {nullptr, nullptr};
+    bool comm_pending[2] = {false, false};       // an all-reduce of publish buffer b is in flight on comm_stream
+    int publish_cur = 0;                         // publish buffer of the last wd_publish_counters (two alternate)
 };
 
 namespace wd {
@@ -164,8 +200,13 @@ int get_seqs(wd_ctx *ctx, int slot, const int64_t *indices, uint32_t n_idx, cons
              int seq_len, uint8_t *codes, uint8_t *pf);
 int count_async(wd_ctx *ctx, int first_slot, int n_tiles, const int32_t *order, int seq_len, int e,
                 int hamming, int mode, int want_per_target);
+int count_trace(wd_ctx *ctx, int first_slot, int n_tiles, const int32_t *order, int seq_len, int e,
+                int hamming, uint32_t *sectors, uint32_t *lines);
+int dup_rows_fetch(wd_ctx *ctx, std::vector<int32_t> &raw);
+int dup_seqs(wd_ctx *ctx, const std::vector<int32_t> &raw, std::vector<uint8_t> &codes);
+int comm_destroy(wd_ctx *ctx);
 int publish_counters(wd_ctx *ctx, const int32_t *tile_row, const int32_t *lane_row, int n_tiles,
-                     int n_rows_total);
+                     int n_rows_total, bool keep);
 int count_exhaustive(wd_ctx *ctx, int slot, const int32_t *order, int seq_len, int levels,
                      uint32_t wlo, uint32_t whi, int e, int hamming, int64_t *tile_counters);
 int upload_descs(wd_ctx *ctx, int first_slot, int n_tiles);

@@ -75,83 +75,63 @@ uint32_t crc32_tables(uint32_t c, const uint8_t *p, size_t n) {
 }
 
 #if defined(__x86_64__)
-// Folding by carry-less multiplication: four 128-bit lanes walk the buffer 64
-// bytes at a time, each folded forward by x^512 mod P; the lanes are merged, the
-// 128-bit remainder is reduced to 32 bits with a Barrett step.  Constants are
-// x^n mod P (bit-reflected) for n = 544, 480, 160, 96, 64 and the Barrett pair
-// (P', mu) of the gzip polynomial.
+// Folding by carry-less multiplication (PCLMULQDQ).  The buffer is read as 128-bit blocks B0 B1 ...; an
+// accumulator A stands for a prefix of the message as a polynomial mod P, and moving it D bits further
+// along is a multiplication by x^D mod P: with A = (lo, hi) the two halves are multiplied separately,
+//     A * x^D  ==  lo * (x^(D+32) mod P)  ^  hi * (x^(D-32) mod P)        (mod P)
+// (the +-32 comes from the 64-bit halves sitting 64 bits apart around the 32-bit remainder, and the
+// product of two bit-reflected 64-bit values comes out one bit low, hence the << 1 below).  Four
+// accumulators walk the buffer 64 bytes at a time (D = 512), are merged with D = 128, the leftover
+// 16-byte blocks are folded in with D = 128 as well -- and what remains is a 16-byte message with the
+// same CRC register as the whole buffer, which the table loop finishes.  The multipliers are computed
+// from the polynomial when first needed, not tabulated.
+struct FoldKeys {
+    __m128i by512, by128;
+};
+
+// x^n mod P in the register's (bit-reflected) order: bit 31 is x^0
+static uint32_t xpow_mod_p(unsigned n) {
+    uint32_t r = 0x80000000u;
+    for (unsigned i = 0; i < n; ++i) r = (r >> 1) ^ ((r & 1u) ? 0xEDB88320u : 0u);
+    return r;
+}
+
+static const FoldKeys &fold_keys() {
+    static const FoldKeys k = [] {
+        auto mult = [](unsigned n) { return (long long)((uint64_t)xpow_mod_p(n) << 1); };
+        FoldKeys f;
+        f.by512 = _mm_set_epi64x(mult(512 - 32), mult(512 + 32));       // high half, low half
+        f.by128 = _mm_set_epi64x(mult(128 - 32), mult(128 + 32));
+        return f;
+    }();
+    return k;
+}
+
+__attribute__((target("pclmul,sse4.1")))
+static inline __m128i fold_into(__m128i acc, __m128i key, __m128i next) {
+    const __m128i lo = _mm_clmulepi64_si128(acc, key, 0x00);
+    const __m128i hi = _mm_clmulepi64_si128(acc, key, 0x11);
+    return _mm_xor_si128(_mm_xor_si128(lo, hi), next);
+}
+
 __attribute__((target("pclmul,sse4.1")))
 uint32_t crc32_clmul(uint32_t c, const uint8_t *p, size_t n) {   // n >= 64, n % 16 == 0
-    const __m128i k1k2 = _mm_set_epi64x(0x01c6e41596, 0x0154442bd4);
-    const __m128i k3k4 = _mm_set_epi64x(0x00ccaa009e, 0x01751997d0);
-    const __m128i k5k0 = _mm_set_epi64x(0x0000000000, 0x0163cd6124);
-    const __m128i poly = _mm_set_epi64x(0x01f7011641, 0x01db710641);
-    __m128i x0, x1, x2, x3, x4, x5, x6, x7, x8, y5, y6, y7, y8;
-    x1 = _mm_loadu_si128((const __m128i *)(p + 0x00));
-    x2 = _mm_loadu_si128((const __m128i *)(p + 0x10));
-    x3 = _mm_loadu_si128((const __m128i *)(p + 0x20));
-    x4 = _mm_loadu_si128((const __m128i *)(p + 0x30));
-    x1 = _mm_xor_si128(x1, _mm_cvtsi32_si128((int)c));
-    x0 = k1k2;
-    p += 64;
-    n -= 64;
-    while (n >= 64) {
-        x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
-        x6 = _mm_clmulepi64_si128(x2, x0, 0x00);
-        x7 = _mm_clmulepi64_si128(x3, x0, 0x00);
-        x8 = _mm_clmulepi64_si128(x4, x0, 0x00);
-        x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
-        x2 = _mm_clmulepi64_si128(x2, x0, 0x11);
-        x3 = _mm_clmulepi64_si128(x3, x0, 0x11);
-        x4 = _mm_clmulepi64_si128(x4, x0, 0x11);
-        y5 = _mm_loadu_si128((const __m128i *)(p + 0x00));
-        y6 = _mm_loadu_si128((const __m128i *)(p + 0x10));
-        y7 = _mm_loadu_si128((const __m128i *)(p + 0x20));
-        y8 = _mm_loadu_si128((const __m128i *)(p + 0x30));
-        x1 = _mm_xor_si128(_mm_xor_si128(x1, x5), y5);
-        x2 = _mm_xor_si128(_mm_xor_si128(x2, x6), y6);
-        x3 = _mm_xor_si128(_mm_xor_si128(x3, x7), y7);
-        x4 = _mm_xor_si128(_mm_xor_si128(x4, x8), y8);
-        p += 64;
-        n -= 64;
-    }
-    // four lanes -> one
-    x0 = k3k4;
-    x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
-    x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
-    x1 = _mm_xor_si128(_mm_xor_si128(x1, x2), x5);
-    x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
-    x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
-    x1 = _mm_xor_si128(_mm_xor_si128(x1, x3), x5);
-    x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
-    x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
-    x1 = _mm_xor_si128(_mm_xor_si128(x1, x4), x5);
-    while (n >= 16) {
-        x2 = _mm_loadu_si128((const __m128i *)p);
-        x5 = _mm_clmulepi64_si128(x1, x0, 0x00);
-        x1 = _mm_clmulepi64_si128(x1, x0, 0x11);
-        x1 = _mm_xor_si128(_mm_xor_si128(x1, x2), x5);
-        p += 16;
-        n -= 16;
-    }
-    // 128 -> 64 bits
-    x2 = _mm_clmulepi64_si128(x1, x0, 0x10);
-    x3 = _mm_setr_epi32(~0, 0, ~0, 0);
-    x1 = _mm_srli_si128(x1, 8);
-    x1 = _mm_xor_si128(x1, x2);
-    x0 = k5k0;
-    x2 = _mm_srli_si128(x1, 4);
-    x1 = _mm_and_si128(x1, x3);
-    x1 = _mm_clmulepi64_si128(x1, x0, 0x00);
-    x1 = _mm_xor_si128(x1, x2);
-    // Barrett reduction to 32 bits
-    x0 = poly;
-    x2 = _mm_and_si128(x1, x3);
-    x2 = _mm_clmulepi64_si128(x2, x0, 0x10);
-    x2 = _mm_and_si128(x2, x3);
-    x2 = _mm_clmulepi64_si128(x2, x0, 0x00);
-    x1 = _mm_xor_si128(x1, x2);
-    return (uint32_t)_mm_extract_epi32(x1, 1);
+    const FoldKeys &k = fold_keys();
+    const __m128i *blk = reinterpret_cast<const __m128i *>(p);
+    size_t left = n / 16;
+    __m128i acc[4];
+    for (int j = 0; j < 4; ++j) acc[j] = _mm_loadu_si128(blk + j);
+    acc[0] = _mm_xor_si128(acc[0], _mm_cvtsi32_si128((int)c));      // the running register enters with the first 4 bytes
+    blk += 4;
+    left -= 4;
+    for (; left >= 4; blk += 4, left -= 4)
+        for (int j = 0; j < 4; ++j) acc[j] = fold_into(acc[j], k.by512, _mm_loadu_si128(blk + j));
+    __m128i a = acc[0];
+    for (int j = 1; j < 4; ++j) a = fold_into(a, k.by128, acc[j]);
+    for (; left > 0; ++blk, --left) a = fold_into(a, k.by128, _mm_loadu_si128(blk));
+    uint8_t tail[16];
+    _mm_storeu_si128(reinterpret_cast<__m128i *>(tail), a);
+    return crc32_tables(0u, tail, sizeof(tail));
 }
 
 bool have_clmul() {

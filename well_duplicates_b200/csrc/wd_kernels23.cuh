@@ -24,13 +24,29 @@ __device__ __forceinline__ int pf_rank(const TileDesc &d, uint32_t well) {
 // s_off[p]  = byte offset of the plane that supplies sequence position p
 // s_kind[p] = WD_PLANE_* of that plane (same for every tile of a launch)
 // one base call -> raw code: 0 = no-call, otherwise base = code & 3
+// A scattered 1-byte read of a plane.  A plain load makes L2 fill the whole 128-byte line from DRAM (4 sectors
+// for 1 useful byte); the 64-byte prefetch-size qualifier is the smallest fill this part offers and halves the
+// DRAM traffic of the gather (profiles/r02_fetch_granularity_micro.txt).
+#ifndef WD_PLANE_LD_L2_64B
+#define WD_PLANE_LD_L2_64B 1
+#endif
+__device__ __forceinline__ uint32_t ld_plane_u8(const uint8_t *p) {
+#if WD_PLANE_LD_L2_64B
+    uint32_t v;
+    asm("ld.global.nc.L2::64B.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+#else
+    return __ldg(p);
+#endif
+}
+
 template <bool ALL_BCL>
 __device__ __forceinline__ uint32_t load_call(const TileDesc &d, uint32_t well, int rank, unsigned long long off,
                                               int kind) {
-    if (ALL_BCL || kind == WD_PLANE_BCL) return __ldg(d.planes + off + well);
+    if (ALL_BCL || kind == WD_PLANE_BCL) return ld_plane_u8(d.planes + off + well);
     const int wi = kind == WD_PLANE_CBCL_EXCL ? rank : (int)well;
     if (wi < 0) return 0u;                        // not PF: the block has no entry for it -> N
-    const uint32_t byte = __ldg(d.planes + off + ((uint32_t)wi >> 1));
+    const uint32_t byte = ld_plane_u8(d.planes + off + ((uint32_t)wi >> 1));
     return (wi & 1) ? (byte >> 4) : (byte & 15u);
 }
 
@@ -218,9 +234,13 @@ struct CountArgs {
     const uint64_t *packed;          // two-pass only
     int32_t *per_target;             // may be null
     unsigned long long *counters;    // [tiles][1+5L]
-    int32_t *dup_rows;               // may be null: (tile, target, csr position, distance)
+    int32_t *dup_rows;               // may be null: (tile, target, slot, distance)
     unsigned long long *dup_count;
     unsigned long long dup_cap;
+    unsigned long long *status;      // [0]: ~(tile << 32 | target) of the first valid target with an empty ring (0: none)
+    uint32_t *trace;                 // measurement build of the fused kernel only: one bit per 32-byte sector read,
+    uint32_t trace_words;            //   [tile][position][trace_words]
+    uint32_t tile_base;              // index, in the caller's batch, of the launch's first tile
     uint32_t t, n_slots;
     int levels, len, e, hamming;
     int step0, step1;                // fused kernel: cycles read per round (first, later), 1..8
@@ -257,7 +277,10 @@ __device__ __forceinline__ void finish_target(const CountArgs &a, uint32_t tile,
     for (int l = 0; l < LMAX; ++l) {
         if (l < L && lane == l) {
             uint32_t *c = s_cnt + 1 + 5 * l;
-            atomicAdd(c + 0, __ldg(a.level_len + (size_t)t * L + l));
+            const uint32_t ring = __ldg(a.level_len + (size_t)t * L + l);
+            // count_well_duplicates.py:249 asserts that a ring holds wells -- for targets that get this far
+            if (ring == 0) atomicMax(a.status, ~(((unsigned long long)(a.tile_base + tile) << 32) | t));
+            atomicAdd(c + 0, ring);
             if (dups[l]) {
                 atomicAdd(c + 1, dups[l]);
                 atomicAdd(c + 2, 1u);
@@ -268,17 +291,17 @@ __device__ __forceinline__ void finish_target(const CountArgs &a, uint32_t tile,
     }
 }
 
+// one row of the duplicate-pair log (count_well_duplicates.py:258-262); rows beyond the buffer are counted only
+__device__ __forceinline__ void log_dup_row(const CountArgs &a, uint32_t tile, uint32_t t, uint32_t slot, int dist) {
+    const unsigned long long pos = atomicAdd(a.dup_count, 1ull);
+    if (pos < a.dup_cap)
+        *reinterpret_cast<int4 *>(a.dup_rows + pos * 4) = make_int4((int)(a.tile_base + tile), (int)t, (int)slot, dist);
+}
+
 template <int W>
 __device__ __forceinline__ void log_dup(const CountArgs &a, uint32_t tile, uint32_t t, uint32_t slot,
                                         const PSeq<W> &c, const PSeq<W> &b) {
-    const unsigned long long pos = atomicAdd(a.dup_count, 1ull);
-    if (pos < a.dup_cap) {
-        int32_t *r = a.dup_rows + pos * 4;
-        r[0] = (int32_t)tile;
-        r[1] = (int32_t)t;
-        r[2] = (int32_t)__ldg(a.slot_csr + slot);
-        r[3] = exact_distance<W>(c, b, a.len, a.hamming != 0);
-    }
+    log_dup_row(a, tile, t, slot, exact_distance<W>(c, b, a.len, a.hamming != 0));
 }
 
 __device__ __forceinline__ void flush_counters(uint32_t *s_cnt, unsigned long long *dst, int n) {
@@ -288,6 +311,12 @@ __device__ __forceinline__ void flush_counters(uint32_t *s_cnt, unsigned long lo
 }
 
 constexpr int CNT_WARPS = 8;
+
+// once per tile: an excluded CBCL block holds exactly the wells that pass the filter (cbcl_read.py:130-131)
+__device__ __forceinline__ void check_excluded_total(const CountArgs &a, const TileDesc &d, uint32_t tile) {
+    if (blockIdx.x == 0 && threadIdx.x == 0 && (d.flags & 2u) && __ldg(d.pfrank + (d.n + 63) / 64) != d.excl_expect)
+        atomicMax(a.status + 1, ~(unsigned long long)(a.tile_base + tile));
+}
 
 // two-pass flavour: reads the packed words K4/K5 left in HBM.  One warp per
 // (tile, target); lanes stride over the target's ring slots.
@@ -300,6 +329,7 @@ compare_count_kernel(CountArgs a) {
     const int lane = threadIdx.x & 31;
     const uint32_t tile = blockIdx.y;
     const uint32_t t = blockIdx.x * CNT_WARPS + (threadIdx.x >> 5);
+    check_excluded_total(a, a.descs[tile], tile);
     if (t < a.t) {
         const uint32_t s0 = __ldg(a.tgt_off + t), s1 = __ldg(a.tgt_off + t + 1);
         const uint64_t *tp = a.packed + (size_t)tile * a.n_slots * (W * PACK_STRIDE);
@@ -363,23 +393,41 @@ __device__ __forceinline__ uint32_t bits_at(const uint64_t *plane, int p, int n)
     return (uint32_t)v & ((1u << n) - 1u);
 }
 
+// measurement build: mark the 32-byte sector of the plane of position `pos` that load_call reads for this well
+template <bool ALL_BCL>
+__device__ __forceinline__ void trace_call(const CountArgs &a, uint32_t tile, int pos, uint32_t well, int rank, int kind) {
+    uint32_t byte = well;
+    if (!(ALL_BCL || kind == WD_PLANE_BCL)) {
+        const int wi = kind == WD_PLANE_CBCL_EXCL ? rank : (int)well;
+        if (wi < 0) return;
+        byte = (uint32_t)wi >> 1;
+    }
+    const uint32_t sec = byte >> 5;              // planes start on 256-byte boundaries
+    atomicOr(a.trace + ((size_t)tile * a.len + pos) * a.trace_words + (sec >> 5), 1u << (sec & 31));
+}
+
 // NMAX calls of one well at sequence positions p .. p+n-1, all loads in flight together
-template <bool ALL_BCL, int NMAX>
-__device__ __forceinline__ void load_calls(const TileDesc &d, uint32_t well, int rank, const unsigned long long *s_off,
-                                           const uint8_t *s_kind, int p, int n, uint32_t (&raw)[NMAX]) {
+template <bool ALL_BCL, int NMAX, bool TRACE>
+__device__ __forceinline__ void load_calls(const CountArgs &a, uint32_t tile, const TileDesc &d, uint32_t well, int rank,
+                                           const unsigned long long *s_off, const uint8_t *s_kind, int p, int n,
+                                           uint32_t (&raw)[NMAX]) {
 #pragma unroll
     for (int j = 0; j < NMAX; ++j) {
         raw[j] = 0u;
-        if (j < n) raw[j] = load_call<ALL_BCL>(d, well, rank, s_off[p + j], ALL_BCL ? 0 : s_kind[p + j]);
+        if (j < n) {
+            raw[j] = load_call<ALL_BCL>(d, well, rank, s_off[p + j], ALL_BCL ? 0 : s_kind[p + j]);
+            if (TRACE) trace_call<ALL_BCL>(a, tile, p + j, well, rank, ALL_BCL ? 0 : s_kind[p + j]);
+        }
     }
 }
 
-template <int W, bool ALL_BCL, int NMAX>
-__device__ __forceinline__ bool ring_round(const TileDesc &d, uint32_t well, int rank, const unsigned long long *s_off,
-                                           const uint8_t *s_kind, const PSeq<W> &c, int known_c, int len, int p, int n,
-                                           int k, int e, bool ham_like, PrefixDP<W> &dp, int &mism) {
+template <int W, bool ALL_BCL, int NMAX, bool TRACE>
+__device__ __forceinline__ bool ring_round(const CountArgs &a, uint32_t tile, const TileDesc &d, uint32_t well, int rank,
+                                           const unsigned long long *s_off, const uint8_t *s_kind, const PSeq<W> &c,
+                                           int known_c, int len, int p, int n, int k, int e, bool ham_like,
+                                           PrefixDP<W> &dp, int &mism) {
     uint32_t raw[NMAX];
-    load_calls<ALL_BCL, NMAX>(d, well, rank, s_off, s_kind, p, n, raw);
+    load_calls<ALL_BCL, NMAX, TRACE>(a, tile, d, well, rank, s_off, s_kind, p, n, raw);
     if (ham_like) {
         uint32_t glo = 0, ghi = 0, gnn = 0;
 #pragma unroll
@@ -409,7 +457,7 @@ __device__ __forceinline__ bool ring_round(const TileDesc &d, uint32_t well, int
     return pdp_band_min<W>(dp, len, p + n, k) <= e;
 }
 
-template <int W, int LMAX, bool ALL_BCL>
+template <int W, int LMAX, bool ALL_BCL, bool TRACE>
 __global__ void __launch_bounds__(CNT_WARPS * 32)
 fused_count_kernel(CountArgs a) {
     __shared__ unsigned long long s_off[MAX_ORDER];
@@ -423,6 +471,7 @@ fused_count_kernel(CountArgs a) {
     const uint32_t tile = blockIdx.y;
     const TileDesc d = a.descs[tile];
     const int len = a.len, e = a.e;
+    if (!ALL_BCL) check_excluded_total(a, d, tile);
     if (a.n_head) {
         // this CTA serves one tile: point its first positions at the tile's head planes
         for (int i = threadIdx.x; i < a.n_head; i += blockDim.x) s_off[i] = d.head_delta + (unsigned long long)i * d.head_stride;
@@ -431,7 +480,8 @@ fused_count_kernel(CountArgs a) {
     // Levenshtein <= 1 <=> Hamming <= 1 on equal lengths (an indel pair costs 2)
     const bool ham_like = a.hamming != 0 || e < 2;
     const int k = ham_like ? 0 : (e >> 1);
-    const bool read_nothing = e < 0 || e >= len;       // no pair / every pair is a duplicate
+    // no pair / every pair is a duplicate -- but the log wants the distance of every duplicate
+    const bool read_nothing = e < 0 || (e >= len && a.dup_rows == nullptr);
     const uint32_t t_begin = blockIdx.x * FUSED_TPB;
     const uint32_t t_end = min(t_begin + FUSED_TPB, a.t);
     // Targets differ a lot in cost (a failed centre costs one byte, a real
@@ -478,8 +528,10 @@ fused_count_kernel(CountArgs a) {
                     while (known_c < need) {
                         const int q = known_c + lane;
                         uint32_t sym = 0u;
-                        if (lane < a.cchunk && q < len)
+                        if (lane < a.cchunk && q < len) {
                             sym = call_symbol(load_call<ALL_BCL>(d, centre, crank, s_off[q], ALL_BCL ? 0 : s_kind[q]));
+                            if (TRACE) trace_call<ALL_BCL>(a, tile, q, centre, crank, ALL_BCL ? 0 : s_kind[q]);
+                        }
                         const uint32_t glo = __ballot_sync(0xffffffffu, sym & 1u);
                         const uint32_t ghi = __ballot_sync(0xffffffffu, sym & 2u);
                         const uint32_t gnn = __ballot_sync(0xffffffffu, sym & 4u);
@@ -490,13 +542,17 @@ fused_count_kernel(CountArgs a) {
                     if (alive) {
                         // three sizes of round are compiled (the schedules that win use 8 + 2 or 8 + 4): a
                         // smaller kernel, fewer instruction-cache misses
-                        if (n > 4) alive = ring_round<W, ALL_BCL, 8>(d, well, rank, s_off, s_kind, c, known_c, len, p, n, k, e, ham_like, dp, mism);
-                        else if (n > 2) alive = ring_round<W, ALL_BCL, 4>(d, well, rank, s_off, s_kind, c, known_c, len, p, n, k, e, ham_like, dp, mism);
-                        else alive = ring_round<W, ALL_BCL, 2>(d, well, rank, s_off, s_kind, c, known_c, len, p, n, k, e, ham_like, dp, mism);
+                        if (n > 4) alive = ring_round<W, ALL_BCL, 8, TRACE>(a, tile, d, well, rank, s_off, s_kind, c, known_c, len, p, n, k, e, ham_like, dp, mism);
+                        else if (n > 2) alive = ring_round<W, ALL_BCL, 4, TRACE>(a, tile, d, well, rank, s_off, s_kind, c, known_c, len, p, n, k, e, ham_like, dp, mism);
+                        else alive = ring_round<W, ALL_BCL, 2, TRACE>(a, tile, d, well, rank, s_off, s_kind, c, known_c, len, p, n, k, e, ham_like, dp, mism);
                     }
                     p += n;
                 }
                 const bool dup = alive;            // survived to p == len: dist <= e
+                // the log: a survivor has been fed every symbol, so the programme holds the exact distance
+                // (at p == len the band minimum is D[len][len]; Lev == Ham where Ham <= 1)
+                if (dup && a.dup_rows != nullptr)
+                    log_dup_row(a, tile, t, s, ham_like ? mism : pdp_band_min<W>(dp, len, len, k));
 #pragma unroll
                 for (int l = 0; l < LMAX; ++l)
                     if (l < a.levels) dups[l] += __popc(__ballot_sync(0xffffffffu, dup && lvl == l + 1));
@@ -545,10 +601,16 @@ void launch_count(wd_ctx *ctx, const CountArgs &a, int n_tiles, int mode, bool a
     dim3 fgrid((a.t + FUSED_TPB - 1) / FUSED_TPB, n_tiles);
     if (mode == 1) {
         compare_count_kernel<W, LMAX><<<grid, CNT_WARPS * 32, 0, ctx->stream>>>(a);
+    } else if (a.trace != nullptr) {
+        // measurement build (wd_count_trace_sectors): one flavour only, the caller has checked that it applies
+        if constexpr (W == 1 && LMAX == 5) {
+            if (all_bcl) fused_count_kernel<1, 5, true, true><<<fgrid, CNT_WARPS * 32, 0, ctx->stream>>>(a);
+            else fused_count_kernel<1, 5, false, true><<<fgrid, CNT_WARPS * 32, 0, ctx->stream>>>(a);
+        }
     } else if (all_bcl) {
-        fused_count_kernel<W, LMAX, true><<<fgrid, CNT_WARPS * 32, 0, ctx->stream>>>(a);
+        fused_count_kernel<W, LMAX, true, false><<<fgrid, CNT_WARPS * 32, 0, ctx->stream>>>(a);
     } else {
-        fused_count_kernel<W, LMAX, false><<<fgrid, CNT_WARPS * 32, 0, ctx->stream>>>(a);
+        fused_count_kernel<W, LMAX, false, false><<<fgrid, CNT_WARPS * 32, 0, ctx->stream>>>(a);
     }
     ctx->launches++;
 }

@@ -96,8 +96,16 @@ static TileDesc make_desc(const TileSlot &s) {
     d.kind = s.kind_dev.as<uint8_t>();
     d.n = s.n;
     d.flags = s.rank_valid ? 1u : 0u;
-    d.head_stride = ((unsigned long long)s.n + 255ull) & ~255ull;
-    d.head_delta = (unsigned long long)(uintptr_t)s.head.as<uint8_t>() - (unsigned long long)(uintptr_t)d.planes;
+    if (s.has_excl && s.rank_valid) {
+        for (int p = 0; p < s.n_planes; ++p)
+            if (s.kind[p] == WD_PLANE_CBCL_EXCL) {
+                d.excl_expect = s.n_block[p];
+                d.flags |= 2u;
+                break;
+            }
+    }
+    d.head_stride = s.head_stride;
+    d.head_delta = (unsigned long long)(uintptr_t)s.head_ptr - (unsigned long long)(uintptr_t)d.planes;
     return d;
 }
 
@@ -127,8 +135,69 @@ __global__ void publish_kernel(const unsigned long long *__restrict__ counters, 
     if (i >= n_tiles * width) return;
     const int tile = i / width, k = i % width;
     const unsigned long long v = counters[i];
-    if (tile_row[tile] >= 0) out[(size_t)tile_row[tile] * width + k] = v;
+    if (tile_row[tile] >= 0) out[(size_t)tile_row[tile] * width + k] = v;      // a row belongs to one tile of one rank
     if (lane_row[tile] >= 0 && v) atomicAdd(out + (size_t)lane_row[tile] * width + k, v);
+}
+
+// ============================================================================
+// duplicate-pair log and the sector trace: small kernels behind wd_dup_pairs_seqs / wd_count_trace_sectors
+// ============================================================================
+// the two sequences of every logged pair, one byte per symbol (0..3 ACGT, 4 N): codes[row][centre, well][len]
+template <bool ALL_BCL>
+__global__ void __launch_bounds__(128)
+dup_seq_kernel(const TileDesc *__restrict__ descs, const int32_t *__restrict__ rows, unsigned long long n_rows,
+               const uint32_t *__restrict__ slot_well, const uint32_t *__restrict__ tgt_off,
+               const unsigned long long *__restrict__ g_off, const uint8_t *__restrict__ g_kind, int len,
+               uint8_t *__restrict__ codes) {
+    __shared__ unsigned long long s_off[MAX_ORDER];
+    __shared__ uint8_t s_kind[MAX_ORDER];
+    load_order(g_off, g_kind, len, s_off, s_kind);
+    const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (i >= 2 * n_rows) return;
+    const int32_t *r = rows + (i >> 1) * 4;
+    const TileDesc d = descs[r[0]];
+    const uint32_t well = __ldg(slot_well + ((i & 1) ? (uint32_t)r[2] : __ldg(tgt_off + r[1])));
+    int rank = 0;
+    if (!ALL_BCL && (d.flags & 1u)) rank = pf_rank(d, well);
+    for (int p = 0; p < len; ++p)
+        codes[i * len + p] = (uint8_t)call_symbol(load_call<ALL_BCL>(d, well, rank, s_off[p], ALL_BCL ? 0 : s_kind[p]));
+}
+
+// sector bitmaps of the measurement build -> per (tile, position): distinct 32-byte sectors, distinct 128-byte lines
+__global__ void __launch_bounds__(256)
+trace_reduce_kernel(const uint32_t *__restrict__ trace, uint32_t words, uint32_t *__restrict__ sectors,
+                    uint32_t *__restrict__ lines) {
+    const uint32_t *row = trace + (size_t)blockIdx.x * words;
+    uint32_t ns = 0, nl = 0;
+    for (uint32_t i = threadIdx.x; i < words; i += blockDim.x) {
+        const uint32_t b = row[i];
+        ns += __popc(b);
+        nl += __popc((b | (b >> 1) | (b >> 2) | (b >> 3)) & 0x11111111u);
+    }
+    __shared__ uint32_t s_ns, s_nl;
+    if (threadIdx.x == 0) s_ns = s_nl = 0;
+    __syncthreads();
+    ns = __reduce_add_sync(0xffffffffu, ns);
+    nl = __reduce_add_sync(0xffffffffu, nl);
+    if ((threadIdx.x & 31) == 0) { atomicAdd(&s_ns, ns); atomicAdd(&s_nl, nl); }
+    __syncthreads();
+    if (threadIdx.x == 0) { sectors[blockIdx.x] = s_ns; lines[blockIdx.x] = s_nl; }
+}
+
+static void launch_dup_seq(wd_ctx *ctx, bool all_bcl, const TileDesc *descs, const int32_t *rows, unsigned long long n_rows,
+                           const uint32_t *slot_well, const uint32_t *tgt_off, int len, uint8_t *codes) {
+    const unsigned long long *g_off = ctx->order_dev.as<unsigned long long>();
+    const uint8_t *g_kind = ctx->order_dev.as<uint8_t>() + (size_t)MAX_ORDER * 8;
+    const unsigned blocks = (unsigned)((2 * n_rows + 127) / 128);
+    if (all_bcl) dup_seq_kernel<true><<<blocks, 128, 0, ctx->stream>>>(descs, rows, n_rows, slot_well, tgt_off, g_off, g_kind, len, codes);
+    else dup_seq_kernel<false><<<blocks, 128, 0, ctx->stream>>>(descs, rows, n_rows, slot_well, tgt_off, g_off, g_kind, len, codes);
+    ctx->launches++;
+}
+
+static void launch_trace_reduce(wd_ctx *ctx, const uint32_t *trace, uint32_t words, uint32_t n_rows, uint32_t *sectors,
+                                uint32_t *lines) {
+    trace_reduce_kernel<<<n_rows, 256, 0, ctx->stream>>>(trace, words, sectors, lines);
+    ctx->launches++;
 }
 
 // ============================================================================
@@ -280,11 +349,64 @@ int get_seqs(wd_ctx *ctx, int slot, const int64_t *indices, uint32_t n_idx, cons
     return WD_OK;
 }
 
-int count_async(wd_ctx *ctx, int first_slot, int n_tiles, const int32_t *order, int seq_len, int e, int hamming,
-                int mode, int want_per_target) {
+static void launch_count_any(wd_ctx *ctx, int words, const CountArgs &a, int n_tiles, int mode, bool all_bcl) {
+    switch (words) {
+        case 1: launch_count_w<1>(ctx, a, n_tiles, mode, all_bcl); break;
+        case 2: launch_count_w<2>(ctx, a, n_tiles, mode, all_bcl); break;
+        case 4: launch_count_w<4>(ctx, a, n_tiles, mode, all_bcl); break;
+        case 8: launch_count_w<8>(ctx, a, n_tiles, mode, all_bcl); break;
+        default: launch_count_w<16>(ctx, a, n_tiles, mode, all_bcl); break;
+    }
+}
+
+// Head planes of host-mapped tiles k0 .. k1-1 -> ctx->head by DMA on the copy stream.  The staging pipeline
+// lays a batch out as [tile][plane][stride] in one page-locked block, so the head planes of a run of tiles are
+// `n_head * stride` contiguous bytes every `pitch` bytes: ONE strided copy per run instead of one per tile and
+// plane (eight GPUs issuing thousands of small copies through one host is what SCALE_r01 showed).
+static int copy_head_planes(wd_ctx *ctx, int first_slot, int k0, int k1, const int32_t *order, int n_head, size_t hstride) {
+    bool consecutive = true;
+    for (int j = 1; j < n_head; ++j) consecutive = consecutive && order[j] == order[0] + j;
+    uint8_t *head = ctx->head.as<uint8_t>();
+    int k = k0;
+    while (k < k1) {
+        const TileSlot &s = ctx->slots[first_slot + k];
+        if (!consecutive || s.stride != hstride) {
+            for (int j = 0; j < n_head; ++j) {
+                const size_t bytes = std::min(s.stride, hstride);
+                WD_CUDA(cudaMemcpyAsync(head + ((size_t)k * n_head + j) * hstride, s.mapped_host + (size_t)order[j] * s.stride, bytes,
+                                        cudaMemcpyHostToDevice, ctx->copy_stream));
+                ctx->last_h2d_bytes += bytes;
+            }
+            ++k;
+            continue;
+        }
+        // longest run of tiles at a constant pitch
+        int run = 1;
+        ptrdiff_t pitch = 0;
+        if (k + 1 < k1) pitch = ctx->slots[first_slot + k + 1].mapped_host - s.mapped_host;
+        if (pitch >= (ptrdiff_t)(n_head * hstride) && pitch < (ptrdiff_t)0x7fffffff) {
+            while (k + run < k1 && ctx->slots[first_slot + k + run].mapped_host - ctx->slots[first_slot + k + run - 1].mapped_host == pitch &&
+                   ctx->slots[first_slot + k + run].stride == hstride)
+                ++run;
+        }
+        const uint8_t *src = s.mapped_host + (size_t)order[0] * s.stride;
+        uint8_t *dst = head + (size_t)k * n_head * hstride;
+        if (run == 1) WD_CUDA(cudaMemcpyAsync(dst, src, (size_t)n_head * hstride, cudaMemcpyHostToDevice, ctx->copy_stream));
+        else WD_CUDA(cudaMemcpy2DAsync(dst, (size_t)n_head * hstride, src, (size_t)pitch, (size_t)n_head * hstride, (size_t)run,
+                                       cudaMemcpyHostToDevice, ctx->copy_stream));
+        ctx->last_h2d_bytes += (uint64_t)run * n_head * hstride;
+        k += run;
+    }
+    return WD_OK;
+}
+
+// mode: WD_MODE_FUSED, WD_MODE_TWO_PASS (logs), WD_MODE_FUSED_LOG; trace != null: measurement build of the fused kernel
+static int count_run(wd_ctx *ctx, int first_slot, int n_tiles, const int32_t *order, int seq_len, int e, int hamming,
+                     int mode, int want_per_target, uint32_t *trace, uint32_t trace_words) {
     TargetList &tl = ctx->targets;
     if (tl.t == 0) WD_FAIL(WD_E_ARG, "wd_count: no target list loaded");
-    if (mode != 0 && mode != 1) WD_FAIL(WD_E_ARG, "wd_count: mode must be 0 (fused) or 1 (two-pass)");
+    if (mode != WD_MODE_FUSED && mode != WD_MODE_TWO_PASS && mode != WD_MODE_FUSED_LOG)
+        WD_FAIL(WD_E_ARG, "wd_count: mode must be 0 (fused), 1 (two-pass) or 2 (fused, duplicate pairs logged)");
     if (n_tiles > 65535) WD_FAIL(WD_E_ARG, "wd_count: at most 65535 tiles per call");
     bool all_bcl, any_excl;
     WD_TRY(prepare_order(ctx, first_slot, n_tiles, order, seq_len, &all_bcl, &any_excl));
@@ -297,68 +419,102 @@ int count_async(wd_ctx *ctx, int first_slot, int n_tiles, const int32_t *order, 
         for (int k = 0; k < n_tiles; ++k) {
             const int id = first_slot + k;
             WD_TRY(filter_rank(ctx, &id, 1));
+            // every excluded block of a tile holds its PF wells (cbcl_read.py:130-131): the kernels compare the
+            // count of the first with the filter's total, so the others have to agree with the first
+            const TileSlot &s = ctx->slots[id];
+            int first = -1;
+            for (int p = 0; p < s.n_planes; ++p) {
+                if (s.kind[p] != WD_PLANE_CBCL_EXCL) continue;
+                if (first < 0) first = p;
+                else if (s.n_block[p] != s.n_block[first])
+                    WD_FAIL(WD_E_ASSERT, "tile slot %d: excluded CBCL blocks of planes %d and %d hold %u and %u clusters", id, first, p,
+                            s.n_block[first], s.n_block[p]);
+            }
         }
     }
-    WD_TRY(upload_descs(ctx, first_slot, n_tiles));
     cudaStream_t st = ctx->stream;
     const int L = tl.levels;
     const size_t width = 1 + 5 * (size_t)L;
-    WD_TRY(ctx->counters.reserve((size_t)n_tiles * width * 8));
-    WD_CUDA(cudaMemsetAsync(ctx->counters.p, 0, (size_t)n_tiles * width * 8, st));
+    ctx->dup_raw_valid = false;
+    const bool fused = mode != WD_MODE_TWO_PASS;
+    const bool logged = mode != WD_MODE_FUSED;
+    const Tuning &tu = ctx->tuning;
+    const bool over_pcie = ctx->slots[first_slot].mapped != nullptr;
+    for (int k = 0; k < n_tiles; ++k)
+        if ((ctx->slots[first_slot + k].mapped != nullptr) != over_pcie)
+            WD_FAIL(WD_E_ARG, "wd_count: host-mapped and staged tile slots cannot share one call");
+
+    // host-mapped tiles: the planes of the first compared positions go to HBM by DMA (below)
+    int n_head = 0, n_groups = 1;
+    size_t hstride = 0;
+    if (fused && over_pcie) {
+        n_head = tu.head_planes >= 0 ? tu.head_planes : 2;          // profiles/r01_schedule_and_staging_sweeps.txt
+        n_head = std::max(0, std::min(n_head, std::min(seq_len, 8)));
+        n_groups = std::max(1, std::min(tu.head_groups > 0 ? tu.head_groups : 16, n_tiles));
+        hstride = ctx->slots[first_slot].stride;          // prepare_order: the same for every tile of the batch
+    }
+    if (n_head > 0) {
+        if ((size_t)n_tiles * n_head * hstride > ctx->head.cap) WD_CUDA(cudaStreamSynchronize(st));
+        WD_TRY(ctx->head.reserve((size_t)n_tiles * n_head * hstride));
+    }
+    for (int k = 0; k < n_tiles; ++k) {
+        TileSlot &s = ctx->slots[first_slot + k];
+        s.head_ptr = n_head > 0 ? ctx->head.as<uint8_t>() + (size_t)k * n_head * hstride : nullptr;
+        s.head_stride = hstride;
+    }
+    WD_TRY(upload_descs(ctx, first_slot, n_tiles));
+
+    // counter rows + two status words behind them
+    WD_TRY(ctx->counters.reserve(((size_t)n_tiles * width + 2) * 8));
+    WD_CUDA(cudaMemsetAsync(ctx->counters.p, 0, ((size_t)n_tiles * width + 2) * 8, st));
     if (want_per_target) WD_TRY(ctx->per_target.reserve((size_t)n_tiles * tl.t * (1 + 2 * L) * 4));
     const int words = words_for(seq_len);
+    if (trace != nullptr && (words != 1 || L > 5))
+        WD_FAIL(WD_E_ARG, "wd_count_trace_sectors: the measurement build covers at most 64 compared symbols and 5 levels");
 
     CountArgs a;
+    memset(&a, 0, sizeof(a));
     a.descs = ctx->descs.as<TileDesc>();
     a.tgt_off = tl.tgt_off.as<uint32_t>();
     a.slot_well = tl.slot_well.as<uint32_t>();
     a.slot_csr = tl.slot_csr.as<uint32_t>();
     a.level_len = tl.level_len.as<uint32_t>();
-    a.visit = getenv("WELLDUP_NO_VISIT_ORDER") ? nullptr : tl.visit.as<uint32_t>();
+    a.visit = tu.visit_order == 0 ? nullptr : tl.visit.as<uint32_t>();
     a.slot_level = tl.slot_level.as<uint8_t>();
     a.g_off = ctx->order_dev.as<unsigned long long>();
     a.g_kind = ctx->order_dev.as<uint8_t>() + (size_t)MAX_ORDER * 8;
-    a.packed = nullptr;
     a.per_target = want_per_target ? ctx->per_target.as<int32_t>() : nullptr;
     a.counters = ctx->counters.as<unsigned long long>();
-    a.dup_rows = nullptr;
-    a.dup_count = nullptr;
-    a.dup_cap = 0;
+    a.status = ctx->counters.as<unsigned long long>() + (size_t)n_tiles * width;
+    a.trace = trace;
+    a.trace_words = trace_words;
     a.t = tl.t;
     a.n_slots = tl.n_slots;
     a.levels = L;
     a.len = seq_len;
     a.e = e;
     a.hamming = hamming;
-    // early-exit schedule of the fused kernel (cycles read per round: first, later), from the sweep
-    // in profiles/r01_early_exit_sweep.txt: short rounds win -- the traffic saved by dropping a well
-    // sooner outweighs the extra dependent round trips
-    // early-exit schedule (cycles read per round: first, later), from the sweeps in profiles/: planes in
-    // HBM are bound by instruction issue and latency -> few long rounds; planes pulled across PCIe
-    // (wd_tile_map_host) are bound by the number of sector requests -> many short rounds
-    const bool over_pcie = ctx->slots[first_slot].mapped != nullptr;
-    a.step0 = over_pcie ? 4 : 8;
+    // early-exit schedule of the fused kernel (cycles read per round: first, later), from the sweeps in
+    // profiles/: planes in HBM are bound by instruction issue and latency -> few long rounds; planes pulled
+    // across PCIe (wd_tile_map_host) are bound by the number of sector requests -> many short rounds
+    a.step0 = over_pcie ? (n_head > 0 ? n_head : 4) : 8;       // host-mapped: the first round entirely from HBM
     a.step1 = over_pcie ? 1 : 4;
     a.cchunk = over_pcie ? 8 : 16;
-    if (const char *cc = getenv("WELLDUP_CENTRE_CHUNK")) {
-        const int v = atoi(cc);
-        if (v == 8 || v == 16 || v == 32) a.cchunk = v;
-    }
-    if (const char *sch = getenv("WELLDUP_STEPS")) {
-        int s0 = 0, s1 = 0;
-        if (sscanf(sch, "%d,%d", &s0, &s1) == 2 && s0 >= 1 && s0 <= 8 && s1 >= 1 && s1 <= 8) {
-            a.step0 = s0;
-            a.step1 = s1;
-        }
-    }
+    if (tu.step0 >= 1 && tu.step0 <= 8) a.step0 = tu.step0;
+    if (tu.step1 >= 1 && tu.step1 <= 8) a.step1 = tu.step1;
+    if (tu.centre_chunk == 8 || tu.centre_chunk == 16 || tu.centre_chunk == 32) a.cchunk = tu.centre_chunk;
+    a.n_head = n_head;
 
-    if (mode == 1) {
+    if (!fused) {
         WD_TRY(ctx->packed.reserve((size_t)n_tiles * tl.n_slots * words * PACK_STRIDE * 8));
-        launch_gather_any(ctx, words, all_bcl, a.descs, a.slot_well, tl.n_slots, n_tiles, seq_len,
-                          ctx->packed.as<uint64_t>());
+        launch_gather_any(ctx, words, all_bcl, a.descs, a.slot_well, tl.n_slots, n_tiles, seq_len, ctx->packed.as<uint64_t>());
         a.packed = ctx->packed.as<uint64_t>();
-        // duplicate-pair log: room for every ring slot of 1/8 of the targets, at least 64k rows
-        size_t cap = (size_t)n_tiles * tl.n_slots / 8 + 65536;
+    }
+    if (logged) {
+        // The log holds what a run of real data produces many times over; a run that produces more (wd_dup_pairs
+        // learns the count) makes wd_dup_pairs grow the buffer and repeat the count -- every pair is logged, as in
+        // the reference, however many there are.
+        const size_t cap = std::max(ctx->dup_cap_wanted, (size_t)n_tiles * tl.n_slots / 8 + 65536);
         WD_TRY(ctx->dup_rows.reserve(cap * 16));
         WD_TRY(ctx->dup_count.reserve(8));
         WD_CUDA(cudaMemsetAsync(ctx->dup_count.p, 0, 8, st));
@@ -369,75 +525,36 @@ int count_async(wd_ctx *ctx, int first_slot, int n_tiles, const int32_t *order, 
     } else {
         ctx->dup_cap = 0;
     }
-    a.n_head = 0;
     ctx->last_h2d_bytes = 0;
-    if (mode == 0 && over_pcie) {
+    if (n_head > 0) {
         // Host-mapped tiles: the planes every ring well is read from -- the first positions -- go to HBM
         // by DMA (bandwidth-bound, ~52 GB/s) while the kernel pulls only what the survivors need of the
-        // later planes as 32-byte sector reads (request-bound, ~0.3 G requests/s): the two limits of the
+        // later planes as 32-byte sector reads (request-bound, ~0.4 G requests/s): the two limits of the
         // PCIe path are used side by side, group of tiles after group of tiles.
-        int n_head = 2, n_groups = 16;              // profiles/r01_notes.md: sweep on the B200 box
-        if (const char *hp = getenv("WELLDUP_HEAD_PLANES")) n_head = atoi(hp);
-        if (const char *hg = getenv("WELLDUP_HEAD_GROUPS")) n_groups = atoi(hg);
-        n_head = std::max(0, std::min(n_head, std::min(seq_len, 8)));
-        for (int k = 0; k < n_tiles; ++k)
-            if (ctx->slots[first_slot + k].mapped == nullptr)
-                WD_FAIL(WD_E_ARG, "wd_count: host-mapped and staged tile slots cannot share one call");
-        if (n_head > 0) {
-            n_groups = std::max(1, std::min(n_groups, n_tiles));
-            a.n_head = n_head;
-            if (!getenv("WELLDUP_STEPS")) {
-                a.step0 = n_head;            // first round entirely from HBM
-                a.step1 = 1;
-            }
-            const size_t hstride = ((size_t)ctx->slots[first_slot].n + 255) & ~(size_t)255;
-            for (int k = 0; k < n_tiles; ++k) WD_TRY(ctx->slots[first_slot + k].head.reserve(hstride * n_head));
-            WD_TRY(upload_descs(ctx, first_slot, n_tiles));       // head pointers may have moved
-            while ((int)ctx->copy_events.size() < n_groups + 1) {
-                cudaEvent_t ev;
-                WD_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
-                ctx->copy_events.push_back(ev);
-            }
-            // the copies may not overtake earlier work on the compute stream that still reads the head buffers
-            WD_CUDA(cudaEventRecord(ctx->copy_events[n_groups], st));
-            WD_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_events[n_groups], 0));
-            const size_t row = 1 + 2 * (size_t)L;
-            for (int g = 0; g < n_groups; ++g) {
-                const int t0 = (int)((long long)n_tiles * g / n_groups), t1 = (int)((long long)n_tiles * (g + 1) / n_groups);
-                for (int k = t0; k < t1; ++k) {
-                    TileSlot &s = ctx->slots[first_slot + k];
-                    for (int j = 0; j < n_head; ++j) {
-                        const int pl = order[j];
-                        const size_t bytes = s.kind[pl] == WD_PLANE_BCL ? (size_t)s.n_block[pl] : ((size_t)s.n_block[pl] + 1) / 2;
-                        WD_CUDA(cudaMemcpyAsync(s.head.as<uint8_t>() + (size_t)j * hstride, s.mapped_host + (size_t)pl * s.stride,
-                                                bytes, cudaMemcpyHostToDevice, ctx->copy_stream));
-                        ctx->last_h2d_bytes += bytes;
-                    }
-                }
-                WD_CUDA(cudaEventRecord(ctx->copy_events[g], ctx->copy_stream));
-                WD_CUDA(cudaStreamWaitEvent(st, ctx->copy_events[g], 0));
-                CountArgs ag = a;
-                ag.descs = a.descs + t0;
-                ag.counters = a.counters + (size_t)t0 * width;
-                if (a.per_target) ag.per_target = a.per_target + (size_t)t0 * tl.t * row;
-                switch (words) {
-                    case 1: launch_count_w<1>(ctx, ag, t1 - t0, mode, all_bcl); break;
-                    case 2: launch_count_w<2>(ctx, ag, t1 - t0, mode, all_bcl); break;
-                    case 4: launch_count_w<4>(ctx, ag, t1 - t0, mode, all_bcl); break;
-                    case 8: launch_count_w<8>(ctx, ag, t1 - t0, mode, all_bcl); break;
-                    default: launch_count_w<16>(ctx, ag, t1 - t0, mode, all_bcl); break;
-                }
-            }
+        while ((int)ctx->copy_events.size() < n_groups + 1) {
+            cudaEvent_t ev;
+            WD_CUDA(cudaEventCreateWithFlags(&ev, cudaEventDisableTiming));
+            ctx->copy_events.push_back(ev);
         }
-    }
-    if (a.n_head == 0) {
-        switch (words) {
-            case 1: launch_count_w<1>(ctx, a, n_tiles, mode, all_bcl); break;
-            case 2: launch_count_w<2>(ctx, a, n_tiles, mode, all_bcl); break;
-            case 4: launch_count_w<4>(ctx, a, n_tiles, mode, all_bcl); break;
-            case 8: launch_count_w<8>(ctx, a, n_tiles, mode, all_bcl); break;
-            default: launch_count_w<16>(ctx, a, n_tiles, mode, all_bcl); break;
+        // the copies may not overtake earlier work on the compute stream that still reads the head buffer
+        WD_CUDA(cudaEventRecord(ctx->copy_events[n_groups], st));
+        WD_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_events[n_groups], 0));
+        const size_t row = 1 + 2 * (size_t)L;
+        for (int g = 0; g < n_groups; ++g) {
+            const int t0 = (int)((long long)n_tiles * g / n_groups), t1 = (int)((long long)n_tiles * (g + 1) / n_groups);
+            WD_TRY(copy_head_planes(ctx, first_slot, t0, t1, order, n_head, hstride));
+            WD_CUDA(cudaEventRecord(ctx->copy_events[g], ctx->copy_stream));
+            WD_CUDA(cudaStreamWaitEvent(st, ctx->copy_events[g], 0));
+            CountArgs ag = a;
+            ag.descs = a.descs + t0;
+            ag.counters = a.counters + (size_t)t0 * width;
+            ag.tile_base = (uint32_t)t0;
+            if (a.per_target) ag.per_target = a.per_target + (size_t)t0 * tl.t * row;
+            if (a.trace) ag.trace = a.trace + (size_t)t0 * seq_len * trace_words;
+            launch_count_any(ctx, words, ag, t1 - t0, 0, all_bcl);
         }
+    } else {
+        launch_count_any(ctx, words, a, n_tiles, fused ? 0 : 1, all_bcl);
     }
     WD_CUDA(cudaGetLastError());
     ctx->last_tiles = n_tiles;
@@ -445,35 +562,153 @@ int count_async(wd_ctx *ctx, int first_slot, int n_tiles, const int32_t *order, 
     ctx->last_t = tl.t;
     ctx->last_first_slot = first_slot;
     ctx->last_per_target = want_per_target != 0;
+    ctx->last_all_bcl = all_bcl;
+    ctx->last_seq_len = seq_len;
     return WD_OK;
 }
 
-int publish_counters(wd_ctx *ctx, const int32_t *tile_row, const int32_t *lane_row, int n_tiles, int n_rows_total) {
-    if (n_tiles != ctx->last_tiles) WD_FAIL(WD_E_ARG, "wd_publish_counters: last wd_count covered %d tiles, not %d", ctx->last_tiles, n_tiles);
-    const int width = 1 + 5 * ctx->last_levels;
+int count_async(wd_ctx *ctx, int first_slot, int n_tiles, const int32_t *order, int seq_len, int e, int hamming,
+                int mode, int want_per_target) {
+    ctx->dup_cap_wanted = 0;
+    WD_TRY(count_run(ctx, first_slot, n_tiles, order, seq_len, e, hamming, mode, want_per_target, nullptr, 0));
+    if (order != ctx->last_order.data()) ctx->last_order.assign(order, order + seq_len);
+    ctx->last_e = e;
+    ctx->last_hamming = hamming;
+    ctx->last_mode = mode;
+    return WD_OK;
+}
+
+// Raw rows (tile, target, slot, distance) of the last logged count, in no particular order.  If there were more
+// pairs than the log had room for, the log is grown to the size the kernels reported and the count is repeated
+// (the tile slots still hold their planes): the reference logs every pair, however many.
+int dup_rows_fetch(wd_ctx *ctx, std::vector<int32_t> &raw) {
+    cudaStream_t st = ctx->stream;
+    if (ctx->dup_raw_valid) {
+        raw = ctx->dup_raw;
+        return WD_OK;
+    }
+    for (int attempt = 0; attempt < 3; ++attempt) {
+        unsigned long long n = 0;
+        WD_CUDA(cudaMemcpyAsync(&n, ctx->dup_count.p, 8, cudaMemcpyDeviceToHost, st));
+        WD_CUDA(cudaStreamSynchronize(st));
+        if (n <= ctx->dup_cap) {
+            raw.resize((size_t)n * 4);
+            if (n) WD_CUDA(cudaMemcpyAsync(raw.data(), ctx->dup_rows.p, (size_t)n * 16, cudaMemcpyDeviceToHost, st));
+            WD_CUDA(cudaStreamSynchronize(st));
+            ctx->dup_raw = raw;
+            ctx->dup_raw_valid = true;
+            return WD_OK;
+        }
+        ctx->dup_cap_wanted = (size_t)n + (size_t)n / 16 + 1024;
+        WD_TRY(count_run(ctx, ctx->last_first_slot, ctx->last_tiles, ctx->last_order.data(), ctx->last_seq_len, ctx->last_e,
+                         ctx->last_hamming, ctx->last_mode, ctx->last_per_target ? 1 : 0, nullptr, 0));
+    }
+    WD_FAIL(WD_E_CAPACITY, "duplicate-pair log kept overflowing");
+}
+
+// codes[row][centre, well][seq_len] for raw rows (same order)
+int dup_seqs(wd_ctx *ctx, const std::vector<int32_t> &raw, std::vector<uint8_t> &codes) {
+    const size_t n = raw.size() / 4;
+    const int len = ctx->last_seq_len;
+    codes.resize(n * 2 * (size_t)len);
+    if (n == 0) return WD_OK;
+    cudaStream_t st = ctx->stream;
+    WD_TRY(ctx->dup_codes.reserve(n * 2 * (size_t)len));
+    // the rows are still in the log buffer, in the order they were fetched in
+    launch_dup_seq(ctx, ctx->last_all_bcl, ctx->descs.as<TileDesc>(), ctx->dup_rows.as<int32_t>(), n,
+                   ctx->targets.slot_well.as<uint32_t>(), ctx->targets.tgt_off.as<uint32_t>(), len, ctx->dup_codes.as<uint8_t>());
+    WD_CUDA(cudaGetLastError());
+    WD_CUDA(cudaMemcpyAsync(codes.data(), ctx->dup_codes.p, codes.size(), cudaMemcpyDeviceToHost, st));
+    WD_CUDA(cudaStreamSynchronize(st));
+    return WD_OK;
+}
+
+// Measurement hook: the fused kernel's reads, recorded.  sectors / lines [n_tiles][seq_len] = distinct 32-byte
+// sectors / 128-byte lines of the plane of each compared position that the kernel asks for, with the schedule
+// and early exits wd_count would use on resident planes.
+int count_trace(wd_ctx *ctx, int first_slot, int n_tiles, const int32_t *order, int seq_len, int e, int hamming,
+                uint32_t *sectors, uint32_t *lines) {
+    if (first_slot < 0 || n_tiles < 1 || (size_t)first_slot + n_tiles > ctx->slots.size())
+        WD_FAIL(WD_E_ARG, "tile slots %d..%d have not been begun", first_slot, first_slot + n_tiles - 1);
+    cudaStream_t st = ctx->stream;
+    size_t max_stride = 0;
+    for (int k = 0; k < n_tiles; ++k) max_stride = std::max(max_stride, ctx->slots[first_slot + k].stride);
+    const uint32_t words = (uint32_t)((max_stride / 32 + 31) / 32);
+    const size_t per_tile = (size_t)seq_len * words * 4;
+    const int chunk = (int)std::max<size_t>(1, std::min<size_t>((size_t)n_tiles, ((size_t)1 << 30) / per_tile));
+    WD_CUDA(cudaStreamSynchronize(st));
+    WD_TRY(ctx->trace.reserve((size_t)chunk * per_tile));
+    WD_TRY(ctx->trace_counts.reserve((size_t)chunk * seq_len * 8));
+    for (int k0 = 0; k0 < n_tiles; k0 += chunk) {
+        const int nk = std::min(chunk, n_tiles - k0);
+        WD_CUDA(cudaMemsetAsync(ctx->trace.p, 0, (size_t)nk * per_tile, st));
+        ctx->dup_cap_wanted = 0;
+        WD_TRY(count_run(ctx, first_slot + k0, nk, order, seq_len, e, hamming, WD_MODE_FUSED, 0, ctx->trace.as<uint32_t>(), words));
+        uint32_t *d_sec = ctx->trace_counts.as<uint32_t>(), *d_lin = d_sec + (size_t)nk * seq_len;
+        launch_trace_reduce(ctx, ctx->trace.as<uint32_t>(), words, (uint32_t)(nk * seq_len), d_sec, d_lin);
+        WD_CUDA(cudaGetLastError());
+        WD_CUDA(cudaMemcpyAsync(sectors + (size_t)k0 * seq_len, d_sec, (size_t)nk * seq_len * 4, cudaMemcpyDeviceToHost, st));
+        WD_CUDA(cudaMemcpyAsync(lines + (size_t)k0 * seq_len, d_lin, (size_t)nk * seq_len * 4, cudaMemcpyDeviceToHost, st));
+        WD_CUDA(cudaStreamSynchronize(st));
+    }
+    ctx->last_tiles = 0;          // the counters of a traced run are not a result to fetch
+    return WD_OK;
+}
+
+// Two buffers alternate, so that the all-reduce of one step (on the communication stream, wd_comm.cc) runs
+// under the counting kernels of the next; `keep` adds to the buffer of the previous call instead (a rank that
+// counts its tiles in several batches publishes each batch into the same rows buffer).
+int publish_counters(wd_ctx *ctx, const int32_t *tile_row, const int32_t *lane_row, int n_tiles, int n_rows_total, bool keep) {
+    // n_tiles == 0: a rank without tiles still brings a zeroed array to the all-reduce
+    if (n_tiles != 0 && n_tiles != ctx->last_tiles)
+        WD_FAIL(WD_E_ARG, "wd_publish_counters: last wd_count covered %d tiles, not %d", ctx->last_tiles, n_tiles);
+    if (ctx->targets.t == 0) WD_FAIL(WD_E_ARG, "wd_publish_counters: no target list loaded");
+    const int width = 1 + 5 * ctx->targets.levels;
     for (int i = 0; i < n_tiles; ++i)
         if (tile_row[i] >= n_rows_total || lane_row[i] >= n_rows_total)
             WD_FAIL(WD_E_ARG, "wd_publish_counters: row index out of range");
     cudaStream_t st = ctx->stream;
     const size_t n = (size_t)n_rows_total * width;
-    const void *before = ctx->publish.p;
-    WD_TRY(ctx->publish.reserve(n * 8 + (size_t)n_tiles * 8));
-    int32_t *rows = reinterpret_cast<int32_t *>(ctx->publish.as<unsigned long long>() + n);
-    WD_CUDA(cudaMemsetAsync(ctx->publish.p, 0, n * 8, st));
+    if (keep && (n != ctx->publish_n || ctx->publish.p == nullptr))
+        WD_FAIL(WD_E_ARG, "wd_publish_add: no buffer of %d rows has been published yet", n_rows_total);
+    if (ctx->pub_ready == nullptr) {
+        WD_CUDA(cudaEventCreateWithFlags(&ctx->pub_ready, cudaEventDisableTiming));
+        for (int b = 0; b < 2; ++b) WD_CUDA(cudaEventCreateWithFlags(&ctx->comm_done[b], cudaEventDisableTiming));
+    }
+    const size_t need = 2 * n * 8 + (size_t)n_tiles * 8;
+    if (need > ctx->publish.cap || n != ctx->publish_n) {
+        // growing frees the old block, another row count moves the second buffer: nothing may still be reading or reducing them
+        WD_CUDA(cudaStreamSynchronize(st));
+        if (ctx->comm_stream) WD_CUDA(cudaStreamSynchronize(ctx->comm_stream));
+        ctx->comm_pending[0] = ctx->comm_pending[1] = false;
+        ctx->publish_map.clear();
+    }
+    WD_TRY(ctx->publish.reserve(need));
+    if (!keep) ctx->publish_cur ^= 1;
+    const int cur = ctx->publish_cur;
+    unsigned long long *buf = ctx->publish.as<unsigned long long>() + (size_t)cur * n;
+    int32_t *rows = reinterpret_cast<int32_t *>(ctx->publish.as<unsigned long long>() + 2 * n);
+    if (ctx->comm_pending[cur]) {
+        WD_CUDA(cudaStreamWaitEvent(st, ctx->comm_done[cur], 0));      // its previous all-reduce has to be over
+        ctx->comm_pending[cur] = false;
+    }
+    if (!keep) WD_CUDA(cudaMemsetAsync(buf, 0, n * 8, st));
     // the row maps are the same step after step (a rank keeps its tiles): upload them when they change only --
     // two small pageable copies cost more than the kernel they feed
     std::vector<int32_t> map(tile_row, tile_row + n_tiles);
     map.insert(map.end(), lane_row, lane_row + n_tiles);
-    if (ctx->publish.p != before || n != ctx->publish_n || map != ctx->publish_map) {
+    if (!map.empty() && (n != ctx->publish_n || map != ctx->publish_map)) {
         WD_CUDA(cudaMemcpyAsync(rows, map.data(), map.size() * 4, cudaMemcpyHostToDevice, st));
         WD_CUDA(cudaStreamSynchronize(st));          // `map` is pageable and local
         ctx->publish_map.swap(map);
     }
     const int total = n_tiles * width;
-    publish_kernel<<<(total + 255) / 256, 256, 0, st>>>(ctx->counters.as<unsigned long long>(), rows, rows + n_tiles,
-                                                         n_tiles, width, ctx->publish.as<unsigned long long>());
-    ctx->launches++;
-    WD_CUDA(cudaGetLastError());
+    if (total > 0) {
+        publish_kernel<<<(total + 255) / 256, 256, 0, st>>>(ctx->counters.as<unsigned long long>(), rows, rows + n_tiles,
+                                                             n_tiles, width, buf);
+        ctx->launches++;
+        WD_CUDA(cudaGetLastError());
+    }
     ctx->publish_n = n;
     return WD_OK;
 }

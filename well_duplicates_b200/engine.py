@@ -98,6 +98,12 @@ class Engine:
         _lib.check(self._lib.wd_set_l2_fetch_granularity(self._h, int(nbytes), C.byref(prev)))
         return prev.value
 
+    def set_tuning(self, step0=0, step1=0, centre_chunk=0, head_planes=-1, head_groups=0, visit_order=-1):
+        """Measurement knobs of wd_count (struct wd_tuning); no arguments = the library's defaults."""
+        t = _lib.Tuning(step0=int(step0), step1=int(step1), centre_chunk=int(centre_chunk), head_planes=int(head_planes),
+                        head_groups=int(head_groups), visit_order=int(visit_order))
+        _lib.check(self._lib.wd_set_tuning(self._h, C.byref(t)))
+
     def launch_count(self):
         n = C.c_uint64()
         _lib.check(self._lib.wd_launch_count(self._h, C.byref(n)))
@@ -214,6 +220,8 @@ class Engine:
         _lib.check(self._lib.wd_count(self._h, first_slot, n_tiles, _ptr(order), order.size, int(edit_distance),
                                       1 if hamming else 0, int(mode), _ptr(pt) if per_target else None,
                                       _ptr(counters)))
+        self._last = (n_tiles, per_target)
+        self._last_len = int(order.size)
         return pt, counters
 
     def count_async(self, first_slot, n_tiles, plane_order, edit_distance=2, hamming=False, mode=0,
@@ -223,6 +231,17 @@ class Engine:
                                             int(edit_distance), 1 if hamming else 0, int(mode),
                                             1 if per_target else 0))
         self._last = (n_tiles, per_target)
+        self._last_len = int(order.size)
+
+    def trace_sectors(self, first_slot, n_tiles, plane_order, edit_distance=2, hamming=False):
+        """Measurement hook (wd_count_trace_sectors): -> (sectors, lines) uint32 [n_tiles, len], the distinct
+        32-byte sectors / 128-byte lines of each compared position's plane the fused kernel reads."""
+        order = _c(plane_order, np.int32)
+        sectors = np.zeros((n_tiles, order.size), np.uint32)
+        lines = np.zeros((n_tiles, order.size), np.uint32)
+        _lib.check(self._lib.wd_count_trace_sectors(self._h, first_slot, n_tiles, _ptr(order), order.size,
+                                                    int(edit_distance), 1 if hamming else 0, _ptr(sectors), _ptr(lines)))
+        return sectors, lines
 
     def count_fetch(self):
         n_tiles, per_target = self._last
@@ -232,26 +251,58 @@ class Engine:
         _lib.check(self._lib.wd_count_fetch(self._h, _ptr(pt) if per_target else None, _ptr(counters)))
         return pt, counters
 
-    def dup_pairs(self):
-        """Rows (tile, target ordinal, well, distance) of the last two-pass count, in
-        the order the reference logs them."""
+    def dup_pairs(self, with_seqs=False):
+        """Rows (tile of the batch, target ordinal, well, distance) of the last count in mode 1 or 2, in the
+        order the reference logs them; with_seqs: also codes uint8 [n, 2, len] (centre, well; 0..3 ACGT, 4 N)."""
         n = C.c_uint64()
-        rc = self._lib.wd_dup_pairs(self._h, None, 0, C.byref(n))
+        rc = self._lib.wd_dup_pairs_seqs(self._h, None, None, 0, C.byref(n))
         if rc not in (_lib.WD_OK, _lib.WD_E_CAPACITY):
             _lib.check(rc)
         rows = np.empty((max(int(n.value), 1), 4), np.int32)
-        _lib.check(self._lib.wd_dup_pairs(self._h, _ptr(rows), rows.shape[0], C.byref(n)))
+        codes = np.empty((rows.shape[0], 2, self._last_len), np.uint8) if with_seqs else None
+        _lib.check(self._lib.wd_dup_pairs_seqs(self._h, _ptr(rows), _ptr(codes) if with_seqs else None, rows.shape[0],
+                                               C.byref(n)))
+        if with_seqs:
+            return rows[: n.value], codes[: n.value]
         return rows[: n.value]
 
-    def publish_counters(self, tile_row, lane_row, n_rows_total):
-        """K7: -> (device pointer, n_int64) of the zero-padded all-reduce buffer."""
+    def publish_counters(self, tile_row, lane_row, n_rows_total, add=False):
+        """K7: -> (device pointer, n_int64) of the zero-padded all-reduce buffer; ``add``: into the
+        buffer of the previous call (a rank that counts its tiles in several batches)."""
         tile_row = _c(tile_row, np.int32)
         lane_row = _c(lane_row, np.int32)
         p = C.c_void_p()
         n = C.c_size_t()
-        _lib.check(self._lib.wd_publish_counters(self._h, _ptr(tile_row), _ptr(lane_row), tile_row.size,
-                                                 int(n_rows_total), C.byref(p), C.byref(n)))
+        fn = self._lib.wd_publish_add if add else self._lib.wd_publish_counters
+        _lib.check(fn(self._h, _ptr(tile_row), _ptr(lane_row), tile_row.size, int(n_rows_total), C.byref(p), C.byref(n)))
         return p.value, n.value
+
+    def comm_join(self):
+        """The engine's stream waits for the all-reduces issued so far."""
+        _lib.check(self._lib.wd_comm_join(self._h))
+
+    # ---- multi-GPU (NCCL inside the library, no torch) -------------------------------------
+    @staticmethod
+    def comm_unique_id():
+        """128 bytes that rank 0 makes and every rank passes to comm_init."""
+        buf = C.create_string_buffer(_lib.COMM_ID_BYTES)
+        _lib.check(_lib.load().wd_comm_unique_id(buf))
+        return buf.raw
+
+    def comm_init(self, unique_id, rank, nranks):
+        _lib.check(self._lib.wd_comm_init(self._h, C.c_char_p(bytes(unique_id)), int(rank), int(nranks)))
+
+    def comm_destroy(self):
+        _lib.check(self._lib.wd_comm_destroy(self._h))
+
+    def allreduce_published(self):
+        """ncclAllReduce(int64, sum), in place, of the buffer of the last publish_counters."""
+        _lib.check(self._lib.wd_allreduce_i64(self._h, None, 0))
+
+    def published_fetch(self, n_int64):
+        out = np.empty(int(n_int64), np.int64)
+        _lib.check(self._lib.wd_published_fetch(self._h, _ptr(out), out.size))
+        return out
 
     def count_exhaustive(self, slot, plane_order, levels=5, edit_distance=2, hamming=False,
                          window_lo=WINDOW_LO, window_hi=WINDOW_HI):

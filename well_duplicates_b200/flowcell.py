@@ -51,26 +51,6 @@ def exchange_host(local_rows, mine, n_lanes, tiles_per_lane, width, dist=None):
     return buf
 
 
-class _DeviceInt64:
-    """Exposes a raw device pointer to torch through __cuda_array_interface__."""
-
-    def __init__(self, ptr, n):
-        self.__cuda_array_interface__ = {"shape": (n,), "typestr": "<i8", "data": (ptr, False), "version": 2}
-
-
-def exchange_device(engine, mine, n_lanes, tiles_per_lane, device, dist=None):
-    """K7 (wd_publish_counters) + ncclAllReduce on the engine's device buffer,
-    for the counters of the engine's last count (its tiles = ``mine``)."""
-    import torch
-    n_tile_rows, n_rows = rows_layout(n_lanes, tiles_per_lane)
-    ptr, n = engine.publish_counters(mine.astype(np.int32), (n_tile_rows + mine // tiles_per_lane).astype(np.int32),
-                                     n_rows)
-    t = torch.as_tensor(_DeviceInt64(ptr, n), device=torch.device("cuda", device))
-    if dist is not None and dist.is_initialized() and dist.get_world_size() > 1:
-        dist.all_reduce(t)
-    return t
-
-
 def print_reports(stream, lanes, tiles, buf, sample_size, levels, verbose):
     """Per-lane reports, in lane order, from the exchanged rows."""
     tpl = len(tiles)
@@ -80,13 +60,17 @@ def print_reports(stream, lanes, tiles, buf, sample_size, levels, verbose):
         write_report(stream, lane, sample_size, [tiles[k] for k in order], [rows[k] for k in order], levels, verbose)
 
 
-def count_rank_tiles(eng, rd, stager, lanes, tiles, mine, wanted, levels, edit_distance, hamming, say=None):
+def count_rank_tiles(eng, rd, stager, lanes, tiles, mine, wanted, levels, edit_distance, hamming, say=None,
+                     publish=False):
     """Counter rows [len(mine), 1 + 5 * levels] of this rank's tiles (``mine`` = ordinals into lanes x tiles).
     Files -> page-locked planes on native threads one batch ahead of the GPU (staging.py); the planes stay in
-    host memory and the fused kernel pulls the sectors it needs (wd_tile_map_host)."""
+    host memory and the fused kernel pulls the sectors it needs (wd_tile_map_host).  ``publish``: every batch's
+    rows are also placed in the engine's exchange buffer on the device (K7, wd_publish_counters / _add), ready
+    for ONE all-reduce after the last batch."""
     from .staging import lane_batches
     rows = np.zeros((len(mine), 1 + 5 * levels), dtype=np.int64)
     names = ["%s/%s" % (lanes[int(o) // len(tiles)], tiles[int(o) % len(tiles)]) for o in mine]
+    n_tile_rows, n_rows = rows_layout(len(lanes), len(tiles))
 
     def open_tile(name):
         lane, tile = name.split("/")
@@ -100,13 +84,17 @@ def count_rank_tiles(eng, rd, stager, lanes, tiles, mine, wanted, levels, edit_d
                 say("Reading tile %s in lane %s" % (tile, lane))
         plane_of = stager.deliver(eng, staged, first_slot=0, zero_copy=True)
         eng.count_async(0, len(got), [plane_of[c] for c in wanted], edit_distance, hamming, mode=0)
+        if publish:
+            part = mine[k:k + len(got)]
+            eng.publish_counters(part.astype(np.int32), (n_tile_rows + part // len(tiles)).astype(np.int32), n_rows, add=k > 0)
         rows[k:k + len(got)] = eng.count_fetch()[1]
         k += len(got)
+    if publish and k == 0:
+        eng.publish_counters(np.zeros(0, np.int32), np.zeros(0, np.int32), n_rows)      # a rank without tiles
     return rows
 
 
 def main(argv=None):
-    import torch
     import torch.distributed as dist
 
     from . import reader as bcl_direct_reader
@@ -117,7 +105,6 @@ def main(argv=None):
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
-    torch.cuda.set_device(local)
     report_stream = sys.stdout
     if world > 1:
         # stdout is the report (a compatibility surface) but native libraries write there too
@@ -126,11 +113,12 @@ def main(argv=None):
         sys.stdout.flush()
         report_stream = os.fdopen(os.dup(1), "w")
         os.dup2(2, 1)
-    if world > 1:
         from .engine import bind_to_gpu_numa_node
         bind_to_gpu_numa_node(local)          # staging memory next to this rank's GPU
-    if world > 1 and not dist.is_initialized():
-        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        if not dist.is_initialized():
+            # rendezvous only (the 128-byte NCCL id, the final barrier): the counters travel by the library's
+            # own ncclAllReduce on device memory (wd_comm_init / wd_allreduce_i64)
+            dist.init_process_group("gloo")
     say = (lambda *a: None) if (args.quiet or rank != 0) else count_cli.log
 
     lanes = args.lane.split(",") if args.lane else [str(x) for x in range(1, 9)]
@@ -139,10 +127,12 @@ def main(argv=None):
     wanted = [c for s, e in cycles for c in range(s, e)]
     targets = load_targets(filename=args.coord_file, levels=args.level + 1, limit=args.sample_size)
     eng = Engine(local)
-    stream = torch.cuda.Stream(device=local)
-    eng.set_stream(stream.cuda_stream)
     centres, level_offsets, idx = targets.to_csr(args.level)
     eng.load_targets(centres, level_offsets, idx, args.level)
+    if world > 1:
+        uid = [Engine.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0)
+        eng.comm_init(uid[0], rank, world)
     rd = bcl_direct_reader.BCLReader(args.run, engine=eng)
 
     mine = plan(len(lanes), len(tiles), rank, world)
@@ -150,22 +140,18 @@ def main(argv=None):
     from .staging import Stager
     stager = Stager(threads=max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world)))),
                     cbcl_cache=rd._cbcl_cache)
-    with torch.cuda.stream(stream):
-        rows = count_rank_tiles(eng, rd, stager, lanes, tiles, mine, wanted, args.level, args.edit_distance,
-                                args.hamming, say)
+    count_rank_tiles(eng, rd, stager, lanes, tiles, mine, wanted, args.level, args.edit_distance, args.hamming, say,
+                     publish=True)
     stager.close()
-    buf = exchange_host(rows, mine, len(lanes), len(tiles), width, dist if world > 1 else None) if world == 1 else None
-    if world > 1:
-        # the counters of many batches live on the host by now: reduce them through a device tensor
-        full = exchange_host(rows, mine, len(lanes), len(tiles), width, None)
-        t = torch.from_numpy(full).to(torch.device("cuda", local))
-        dist.all_reduce(t)                      # ncclAllReduce(int64, sum) over NVLink
-        buf = t.cpu().numpy()
+    # K7 has put every batch's rows into the exchange buffer on the device: one ncclAllReduce(int64, sum) over NVLink
+    eng.allreduce_published()
+    buf = eng.published_fetch(rows_layout(len(lanes), len(tiles))[1] * width).reshape(-1, width)
     if rank == 0:
         print_reports(report_stream, lanes, tiles, buf, len(targets), args.level, verbose=not args.summary_only)
         report_stream.flush()
     if world > 1:
         dist.barrier()
+        eng.comm_destroy()
         dist.destroy_process_group()
 
 

@@ -140,7 +140,8 @@ class Stager:
         from .reader import CbclFile
         uniq = sorted(set(cycles))
         n = tiles[0].num_clusters
-        assert all(t.num_clusters == n for t in tiles)
+        if not all(t.num_clusters == n for t in tiles):
+            raise ValueError("the tiles of one batch must have the same cluster count")
         stride = _round_up(n + BCL_HEADER, 256)
         fstride = _round_up(n, 256)
         self.reserve(which, n, len(tiles), len(uniq))        # no-op when lane_batches made room already
@@ -151,7 +152,8 @@ class Stager:
         for k, t in enumerate(tiles):
             view = block.array[LEAD + len(tiles) * len(uniq) * stride + k * fstride:][:fstride]
             with open(t.filter_file, "rb") as fh:
-                assert struct.unpack("<III", fh.read(12)) == (0, 3, n)
+                if struct.unpack("<III", fh.read(12)) != (0, 3, n):          # bcl_direct_reader.py:146-152
+                    raise AssertionError("%s: filter header is not (0, 3, %d)" % (t.filter_file, n))
                 got = fh.readinto(memoryview(view[:n]))
             view[got:] = 0
         # planes: BCL first ...
@@ -173,9 +175,11 @@ class Stager:
             cf = self._cbcl_cache.get(path)
             if cf is None:
                 cf = self._cbcl_cache[path] = CbclFile(path)
-            assert int(t.tile) in cf.blocks
+            if int(t.tile) not in cf.blocks:
+                raise AssertionError("%s holds no block for tile %s" % (path, t.tile))
             off, ncl, usize, csize = cf.blocks[int(t.tile)]
-            assert usize <= stride, "CBCL block of %d bytes for a tile of %d clusters" % (usize, n)
+            if usize > stride:
+                raise AssertionError("CBCL block of %d bytes for a tile of %d clusters" % (usize, n))
             cjobs.append((path, off, csize, row, usize))
             cwhere.append((k, p, ncl, usize, cf.excluded))
         cres = self._run(cjobs)
@@ -187,7 +191,8 @@ class Stager:
                 # GzipFile.read(usize) stops after usize bytes whatever follows (bcl_direct_reader.py:301)
                 if cj.status not in (_lib.WD_OK, _lib.WD_E_CAPACITY):
                     _lib.raise_status(cj.status, cj.message.decode("utf-8", "replace"))
-                assert cj.out_len * 2 >= ncl, "CBCL block of %d bytes cannot hold %d clusters" % (cj.out_len, ncl)
+                if cj.out_len * 2 < ncl:
+                    raise AssertionError("CBCL block of %d bytes cannot hold %d clusters" % (cj.out_len, ncl))
                 batch.kinds[k, p] = _lib.PLANE_CBCL_EXCL if excl else _lib.PLANE_CBCL
                 batch.n_block[k, p] = ncl
                 batch.usize[k, p] = cj.out_len
@@ -196,11 +201,14 @@ class Stager:
                 continue
             if j.status not in (_lib.WD_OK, _lib.WD_E_CAPACITY):
                 _lib.raise_status(j.status, j.message.decode("utf-8", "replace"))
-            assert j.out_len >= BCL_HEADER
             off = row - BCL_HEADER - base
-            (count,) = struct.unpack("<I", block.array[off:off + BCL_HEADER].tobytes())
-            assert count == n                                    # bcl_direct_reader.py:338
-            assert j.out_len == n + BCL_HEADER, "BCL file holds %d calls, header says %d" % (j.out_len - BCL_HEADER, n)
+            (count,) = struct.unpack("<I", block.array[off:off + BCL_HEADER].tobytes()) if j.out_len >= BCL_HEADER else (None,)
+            if count != n:                                       # bcl_direct_reader.py:338
+                raise AssertionError("BCL header says %s clusters, filter says %d" % (count, n))
+            # stricter than the reference, which fails only when a requested well lies beyond the data it got:
+            # a plane that is not exactly one call per well is refused (intentional divergences)
+            if j.out_len != n + BCL_HEADER:
+                raise AssertionError("BCL file holds %d calls, header says %d" % (j.out_len - BCL_HEADER, n))
             batch.inflated_bytes += int(j.out_len)
         return batch
 
@@ -228,24 +236,30 @@ class Stager:
         return dict(batch.plane_of)
 
 
-def lane_batches(stager, open_tile, names, cycles, per_batch=None, announce=None):
-    """Walks ``names`` (tile names of one lane, in order): yields (names of the batch,
-    StagedBatch) while the following batch is read and inflated in the background.
+def lane_batches(stager, open_tile, names, cycles, per_batch=None, announce=None, on_error=None):
+    """Walks ``names`` (tile names, in order): yields (names of the batch, StagedBatch)
+    while the following batch is read and inflated in the background.
     ``open_tile(name)`` -> reader.Tile.  A batch holds tiles of one cluster count, at
     most ``per_batch`` of them (default: what the pinned budget allows).
     ``announce(name)`` is called for each tile just before its batch is waited for --
     with per_batch=1 that is the moment the reference logs "Reading tile".
-    An error met while preparing batch k+1 is raised when batch k+1 is due, after
-    batch k has been handed out: the order in which the reference would hit it."""
+    Errors surface where the reference would meet them (count_well_duplicates.py:207-226
+    walks tile by tile): every tile in front of the failing one is handed out first -- a
+    tile that cannot be opened ends its batch early and the error is kept for the next
+    round; a batch whose files fail to load is loaded again tile by tile -- and
+    ``on_error(name)`` is called with the failing tile just before the exception is raised."""
     uniq = sorted(set(cycles))
+    pending = {}                           # index of a tile that failed to open -> its exception
 
-    def prepare(start, which):
+    def prepare(start, which, limit=None):
         """Caller's thread: open the tiles of the next batch, make room for them (page-locked
         memory is allocated on the thread that owns the CUDA device), start the inflate."""
         tiles = []
+        if start in pending:
+            return tiles, None, pending.pop(start)
+        limit = per_batch if limit is None else limit
+        k = start
         try:
-            limit = per_batch
-            k = start
             while k < len(names):
                 t = open_tile(names[k])
                 if tiles and t.num_clusters != tiles[0].num_clusters:
@@ -258,9 +272,20 @@ def lane_batches(stager, open_tile, names, cycles, per_batch=None, announce=None
                     break
             if tiles:
                 stager.reserve(which, tiles[0].num_clusters, len(tiles), len(uniq))
-        except Exception as exc:           # noqa: BLE001 -- re-raised when this batch is due
-            return tiles, None, exc
+        except Exception as exc:           # noqa: BLE001 -- raised when the failing tile is due
+            if not tiles:
+                return tiles, None, exc
+            pending[k] = exc               # the tiles opened so far are a batch of their own
+            try:
+                stager.reserve(which, tiles[0].num_clusters, len(tiles), len(uniq))
+            except Exception as exc2:      # noqa: BLE001
+                return [], None, exc2
         return tiles, (stager.load_async(tiles, uniq, which) if tiles else None), None
+
+    def fail(name, exc):
+        if on_error is not None:
+            on_error(name)
+        raise exc
 
     start, which = 0, 0
     tiles, fut, err = prepare(start, which)
@@ -268,8 +293,25 @@ def lane_batches(stager, open_tile, names, cycles, per_batch=None, announce=None
         if announce is not None and per_batch == 1:
             announce(names[start])
         if err is not None:
-            raise err
-        batch = fut.result()
+            fail(names[start], err)
+        try:
+            batch = fut.result()
+        except Exception as exc:           # noqa: BLE001
+            if len(tiles) == 1:
+                fail(names[start], exc)
+            # some file of the batch is bad: tile by tile, so that the good ones in front of it are counted
+            for k in range(start, start + len(tiles)):
+                one, f1, e1 = prepare(k, which, limit=1)
+                if e1 is not None:
+                    fail(names[k], e1)
+                try:
+                    b1 = f1.result()
+                except Exception as exc1:  # noqa: BLE001
+                    fail(names[k], exc1)
+                yield names[k:k + 1], b1
+            start += len(tiles)            # (every tile loaded on its own: carry on)
+            tiles, fut, err = prepare(start, which)
+            continue
         got = names[start:start + len(tiles)]
         start += len(tiles)
         which ^= 1
