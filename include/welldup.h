@@ -91,7 +91,7 @@ WD_API int wd_launch_count(wd_ctx *ctx, uint64_t *out);
  * NULL restores every default.  The library reads no environment variables. */
 typedef struct wd_tuning {
     int32_t step0, step1;  /* cycles the fused kernel reads per round (first round, later rounds), 1..8 */
-    int32_t centre_chunk;  /* centre cycles decoded per warp-wide load: 8, 16 or 32 */
+    int32_t centre_chunk;  /* 8, 16 or 32: the centre is read ahead to a multiple of this many cycles (default: exactly as far as needed) */
     int32_t head_planes;   /* host-mapped tiles: compared positions whose planes are copied to HBM by DMA, 0..8; -1 default */
     int32_t head_groups;   /* ... in how many tile groups, pipelined against the counting kernels */
     int32_t visit_order;   /* 0: targets in list order; 1 or -1: in ascending order of their centre well */

@@ -74,7 +74,16 @@ static void prefix_dp(const uint8_t *a, const uint8_t *b, int len, int k, int ch
         }
         // the kernel's dispatch: rounds inside the first 32 rows take the word-0 forms
         if (wd::pdp_round_in_word0(p, 1, k)) {
+            wd::PrefixDP<W> s2 = s;
             wd::pdp_step_word0<W>(s, (uint32_t)pa.lo[0], (uint32_t)pa.hi[0], (uint32_t)pa.nn[0], wd::len_mask32(known, 0), b[p]);
+            // ... and with the Eq mask looked up per symbol, as the kernel keeps it in shared memory
+            uint32_t eq[5];
+            for (unsigned c = 0; c < 5; ++c) {
+                const uint32_t tlo = (c & 1u) ? ~0u : 0u, thi = (c & 2u) ? ~0u : 0u, tn = (c & 4u) ? ~0u : 0u;
+                eq[c] = ~(((uint32_t)pa.lo[0] ^ tlo) | ((uint32_t)pa.hi[0] ^ thi) | ((uint32_t)pa.nn[0] ^ tn)) & wd::len_mask32(known, 0);
+            }
+            wd::pdp_step_word0_eq<W>(s2, eq[b[p]]);
+            if (s2.Pv[0] != s.Pv[0] || s2.Mv[0] != s.Mv[0]) { out[p + 1] = -2000; continue; }
             out[p + 1] = wd::pdp_band_min_word0<W>(s, len, p + 1, k);
             if (out[p + 1] != wd::pdp_band_min<W>(s, len, p + 1, k)) out[p + 1] = -1000;     // the two forms must agree
         } else {

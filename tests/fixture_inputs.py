@@ -108,7 +108,17 @@ COUNT_CASES = [
     ("cbcl_odd", "run_cbcl", _CBCL + ["-t", "1102", "-l", "5", "--cycles", "3-12"]),
     ("cbcl_early", "run_cbcl", _CBCL + ["-t", "1101", "-l", "5", "--cycles", "0-6"]),
     ("cbcl_late", "run_cbcl", _CBCL + ["-t", "1101", "-l", "5", "--cycles", "6-14"]),
+    # lane 3 does not exist: the reference prints the reports of lanes 1 and 2, logs "Reading tile" for the
+    # tile it cannot open and dies with FileNotFoundError
+    ("missing_lane", "run_bcl", ["-s", "hiseq_x", "-i", "1,2,3", "-t", "1101", "-l", "5", "--cycles", "0-14"]),
+    # ... and a tile without a .filter file in the middle of a lane: RuntimeError after the tiles in front of it
+    ("missing_tile", "run_bcl", ["-s", "hiseq_x", "-i", "1", "-t", "110[1-4]", "-l", "5", "--cycles", "0-14"]),
 ]
+
+# the per-lane report files a workflow run leaves behind (Snakefile.count_and_push:174-181), for the
+# all-lanes summary (`tail`, :166-172) and the two wiki formatters that parse it (:183-197)
+WIKI_LANES = [("1", ["-s", "hiseq_x", "-i", "1", "-t", "1101,1102", "-l", "5", "--cycles", "0-14"]),
+              ("2", ["-s", "hiseq_x", "-i", "2", "-t", "1101", "-l", "5", "--cycles", "0-14", "-S"])]
 
 
 def getseqs_cases():

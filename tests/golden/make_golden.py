@@ -102,6 +102,12 @@ def main():
         out = os.path.join(locs_dir, tag + ".list")
         with open(out, "w") as fh:
             fh.write(p.stdout)
+        # the chatter on stderr (seed, sample, the byte offset of every scan); a run that dies: up to its traceback
+        perr = strip_warnings(p.stderr)
+        if p.returncode != 0:
+            perr = perr.split("Traceback (most recent call last)")[0]
+        with open(os.path.join(locs_dir, tag + ".stderr"), "w") as fh:
+            fh.write(perr)
         manifest["prepare"].append({"locs": name, "n": n, "seed": seed, "returncode": p.returncode,
                                     "list": os.path.relpath(out, HERE),
                                     "error": ("RuntimeError" if "RuntimeError" in p.stderr else None)})
@@ -147,11 +153,41 @@ def main():
         err = strip_warnings(p.stderr)
         with open(os.path.join(out_dir, name + ".stdout"), "w") as fh:
             fh.write(p.stdout)
+        # a run that dies: the log up to the traceback (whose paths are the container's), then the exception line
+        raises = None
+        if p.returncode != 0:
+            raises = err.strip().splitlines()[-1].split(":")[0]
+            err = err.split("Traceback (most recent call last)")[0] + err.strip().splitlines()[-1].split(":")[0] + "\n"
         with open(os.path.join(out_dir, name + ".stderr"), "w") as fh:
-            fh.write(err if p.returncode == 0 else err[-2000:])
+            fh.write(err)
         manifest["count"].append({"name": name, "run": run, "args": list(map(str, extra)),
-                                  "targets": targets, "returncode": p.returncode})
+                                  "targets": targets, "returncode": p.returncode, "raises": raises})
         print("count", name, "rc", p.returncode, "stdout lines", p.stdout.count("\n"))
+
+    # ---- the callers behind the report: all-lanes summary (GNU tail) and the two wiki formatters ----------
+    wiki_dir = os.path.join(HERE, "wiki")
+    shutil.rmtree(wiki_dir, ignore_errors=True)
+    os.makedirs(wiki_dir)
+    lane_files = []
+    for lane, extra in fx.WIKI_LANES:
+        p = run_ref("count_well_duplicates.py", ["-f", tf, "-r", run_bcl, "-q"] + list(extra))
+        assert p.returncode == 0, p.stderr
+        lane_files.append("40targets_lane%s.txt" % lane)
+        with open(os.path.join(wiki_dir, lane_files[-1]), "w") as fh:
+            fh.write(p.stdout)
+    for tag, n in (("all_lanes", 5 + 1), ("all_lanes_plus4", 5 + 4)):       # Snakefile.count_dups:151, Snakefile.count_and_push:172
+        p = subprocess.run(["tail", "-n", str(n)] + lane_files, capture_output=True, text=True, cwd=wiki_dir)
+        assert p.returncode == 0, p.stderr
+        with open(os.path.join(wiki_dir, "40targets_%s.txt" % tag), "w") as fh:
+            fh.write(p.stdout)
+        for script, ext in (("summary_to_wiki.py", "wiki"), ("summary_to_wiki2.py", "wiki2.html")):
+            q = subprocess.run([sys.executable, os.path.join(REF, script)], input=p.stdout, capture_output=True, text=True, env=ENV)
+            assert q.returncode == 0, q.stderr
+            with open(os.path.join(wiki_dir, "40targets_%s.%s" % (tag, ext)), "w") as fh:
+                fh.write(q.stdout)
+    manifest["wiki"] = {"lanes": [[lane, list(map(str, extra))] for lane, extra in fx.WIKI_LANES], "run": "run_bcl",
+                        "targets": targets, "levels": 5}
+    print("wiki", sorted(os.listdir(wiki_dir)))
 
     # ---- stage 2: get_seqs ------------------------------------------------
     gs_dir = os.path.join(HERE, "getseqs")

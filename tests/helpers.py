@@ -63,3 +63,36 @@ def parse_count_args(args):
     else:
         o["ranges"] = [(o["x"], o["y"])]
     return o
+
+
+_EXC = {"ZeroDivisionError": ZeroDivisionError, "FileNotFoundError": FileNotFoundError, "RuntimeError": RuntimeError,
+        "IndexError": IndexError, "AssertionError": AssertionError}
+
+
+def run_count_case(main, case, extra=()):
+    """Runs a count CLI ``main(argv)`` on a golden case -> (stdout, stderr); a case the reference dies on must
+    die here with the same exception type (manifest "raises")."""
+    import contextlib
+    import io
+
+    import pytest
+    argv = ["-f", os.path.join(GOLDEN, case["targets"]), "-r", os.path.join(GOLDEN, case["run"])] + case["args"] + list(extra)
+    out, err = io.StringIO(), io.StringIO()
+    with contextlib.redirect_stdout(out), contextlib.redirect_stderr(err):
+        if case["returncode"] != 0:
+            with pytest.raises(_EXC[case.get("raises") or "ZeroDivisionError"]):
+                main(argv)
+        else:
+            main(argv)
+    return out.getvalue(), err.getvalue()
+
+
+def golden_count_output(case):
+    """(stdout, log) of the unmodified reference; for a run that died the log ends where its traceback began."""
+    with open(os.path.join(GOLDEN, "count", case["name"] + ".stdout")) as fh:
+        out = fh.read()
+    with open(os.path.join(GOLDEN, "count", case["name"] + ".stderr")) as fh:
+        err = fh.read()
+    if case["returncode"] != 0:
+        err = err[:err.rstrip("\n").rfind("\n") + 1]          # drop the exception line
+    return out, err

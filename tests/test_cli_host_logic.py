@@ -14,7 +14,7 @@ import os
 import numpy as np
 import pytest
 
-from helpers import GOLDEN, load_manifest
+from helpers import GOLDEN, golden_count_output, load_manifest, run_count_case
 from oracle import c_port as CP
 from well_duplicates_b200 import _lib, count_cli, reader, staging
 
@@ -132,21 +132,10 @@ def oracle_engine(monkeypatch):
 
 @pytest.mark.parametrize("case", MAN["count"], ids=lambda c: c["name"])
 def test_count_cli_host_side_matches_reference(case, oracle_engine):
-    with open(os.path.join(GOLDEN, "count", case["name"] + ".stdout")) as fh:
-        want_out = fh.read()
-    with open(os.path.join(GOLDEN, "count", case["name"] + ".stderr")) as fh:
-        want_err = fh.read()
-    argv = ["-f", os.path.join(GOLDEN, case["targets"]), "-r", os.path.join(GOLDEN, case["run"])] + case["args"]
-    out, err = io.StringIO(), io.StringIO()
-    with contextlib.redirect_stdout(out), contextlib.redirect_stderr(err):
-        if case["returncode"] != 0:
-            with pytest.raises(ZeroDivisionError):
-                count_cli.main(argv)
-        else:
-            count_cli.main(argv)
-    assert out.getvalue() == want_out
-    if case["returncode"] == 0:
-        assert err.getvalue() == want_err
+    want_out, want_err = golden_count_output(case)
+    out, err = run_count_case(count_cli.main, case)
+    assert out == want_out
+    assert err == want_err
     quiet = "-q" in case["args"] or "--quiet" in case["args"]
     # the planes stay where the inflate put them; without -q the fused kernel also logs the duplicate pairs
     assert set(oracle_engine.calls) == {"map"}
@@ -209,19 +198,9 @@ def test_quiet_run_prints_the_reference_report_from_counter_rows(case, oracle_en
     (report.write_report) instead of the per-target lists: same stdout as the reference for every
     golden case -- the stdout of count_well_duplicates.py does not depend on -q -- including the lane
     without hits that ends in ZeroDivisionError after its per-tile lines."""
-    with open(os.path.join(GOLDEN, "count", case["name"] + ".stdout")) as fh:
-        want_out = fh.read()
-    argv = ["-f", os.path.join(GOLDEN, case["targets"]), "-r", os.path.join(GOLDEN, case["run"])] + case["args"]
-    if "-q" not in argv:
-        argv.append("-q")
-    out, err = io.StringIO(), io.StringIO()
-    with contextlib.redirect_stdout(out), contextlib.redirect_stderr(err):
-        if case["returncode"] != 0:
-            with pytest.raises(ZeroDivisionError):
-                count_cli.main(argv)
-        else:
-            count_cli.main(argv)
-    assert out.getvalue() == want_out and err.getvalue() == ""
+    want_out, _ = golden_count_output(case)
+    out, err = run_count_case(count_cli.main, case, extra=[] if "-q" in case["args"] else ["-q"])
+    assert out == want_out and err == ""
     assert set(oracle_engine.calls) == {"map"}
 
 
@@ -248,3 +227,27 @@ def test_quiet_lane_without_any_valid_target(tmp_path, oracle_engine):
         with contextlib.redirect_stdout(out), contextlib.redirect_stderr(err):
             count_cli.main(["-f", target_file, "-r", run, "-s", "1102", "-i", "1", "--cycles", "0-8"] + flags)
         assert out.getvalue() == want
+
+
+def test_report_text_feeds_the_wiki_formatters(tmp_path, oracle_engine):
+    """The stdout of the drop-in CLI is a compatibility surface: the reference's summary_to_wiki.py /
+    summary_to_wiki2.py parse it (through `tail`).  Lane reports written by count_cli -> summarize_all_lanes ->
+    the formatters give exactly what the unmodified scripts made of the reference's own reports."""
+    import wiki_formatters as W
+    from well_duplicates_b200 import workflow as wf
+    wiki = os.path.join(GOLDEN, "wiki")
+    lane_files = []
+    for lane, args in MAN["wiki"]["lanes"]:
+        out = io.StringIO()
+        with contextlib.redirect_stdout(out):
+            count_cli.main(["-f", os.path.join(GOLDEN, MAN["wiki"]["targets"]), "-r", os.path.join(GOLDEN, MAN["wiki"]["run"]), "-q"] + args)
+        path = tmp_path / ("40targets_lane%s.txt" % lane)
+        path.write_text(out.getvalue())
+        with open(os.path.join(wiki, path.name)) as fh:
+            assert out.getvalue() == fh.read()
+        lane_files.append(str(path))
+    for tag, extra in (("all_lanes", 0), ("all_lanes_plus4", 3)):
+        text = wf.summarize_all_lanes(lane_files, levels=5, extra=extra, names=[os.path.basename(p) for p in lane_files])
+        for fn, ext in ((W.to_wiki, "wiki"), (W.to_wiki2, "wiki2.html")):
+            with open(os.path.join(wiki, "40targets_%s.%s" % (tag, ext))) as fh:
+                assert fn(text) == fh.read()

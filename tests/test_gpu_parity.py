@@ -42,19 +42,33 @@ def test_k0_pixels(eng, oracle, name, tmp_path):
 
 @pytest.mark.parametrize("case", MAN["prepare"], ids=lambda c: "%s_n%d_s%s" % (c["locs"], c["n"], c["seed"]))
 def test_prepare_cli_byte_identical(case, tmp_path, capsys):
-    """prepare_cluster_indexes drop-in: stdout equals the reference's target file."""
-    from well_duplicates_b200 import prepare_cli
+    """prepare_cluster_indexes drop-in: stdout equals the reference's target file, stderr its chatter (seed,
+    sample, the byte offset logged for every scan; up to the traceback when the reference dies on an empty ring);
+    --binary writes the same list as arrays that convert back to the byte-identical text."""
+    import io
+
+    from well_duplicates_b200 import prepare_cli, targets
     path = locs_path(case["locs"], tmp_path)
     with open(os.path.join(GOLDEN, case["list"])) as fh:
         want = fh.read()
+    with open(os.path.join(GOLDEN, case["list"][:-len(".list")] + ".stderr")) as fh:
+        want_err = fh.read()
     argv = ["-f", path, "-n", str(case["n"])] + (["-s", str(case["seed"])] if case["seed"] is not None else [])
     if case["returncode"] != 0:
         with pytest.raises(RuntimeError, match="Got no wells"):
             prepare_cli.main(argv)
-        assert capsys.readouterr().out == ""
+        got = capsys.readouterr()
+        assert got.out == "" and got.err == want_err
         return
     prepare_cli.main(argv)
-    assert capsys.readouterr().out == want
+    got = capsys.readouterr()
+    assert got.out == want and got.err == want_err
+    binary = str(tmp_path / "targets.bin")
+    prepare_cli.main(argv + ["--binary", binary])
+    assert capsys.readouterr().out == ""
+    text = io.StringIO()
+    targets.binary_to_text(binary, text)
+    assert text.getvalue() == want
 
 
 def test_ring_query_every_well_vs_oracle(eng, oracle, tmp_path):
@@ -140,22 +154,48 @@ def test_k3_rank_large_random(eng, oracle):
 def test_count_cli_matches_reference(case):
     """count_well_duplicates drop-in: stdout (report) and stderr (log with every
     duplicate pair) equal the reference's."""
+    from helpers import golden_count_output, run_count_case
     from well_duplicates_b200 import count_cli
-    with open(os.path.join(GOLDEN, "count", case["name"] + ".stdout")) as fh:
-        want_out = fh.read()
-    with open(os.path.join(GOLDEN, "count", case["name"] + ".stderr")) as fh:
-        want_err = fh.read()
-    argv = ["-f", os.path.join(GOLDEN, case["targets"]), "-r", os.path.join(GOLDEN, case["run"])] + case["args"]
-    out, err = io.StringIO(), io.StringIO()
-    with contextlib.redirect_stdout(out), contextlib.redirect_stderr(err):
-        if case["returncode"] != 0:
-            with pytest.raises(ZeroDivisionError):
-                count_cli.main(argv)
-        else:
-            count_cli.main(argv)
-    assert out.getvalue() == want_out
-    if case["returncode"] == 0:
-        assert err.getvalue() == want_err
+    want_out, want_err = golden_count_output(case)
+    out, err = run_count_case(count_cli.main, case)
+    assert out == want_out
+    assert err == want_err
+
+
+@pytest.mark.parametrize("name", ["lev_default", "limit10", "xy_l3", "cbcl_default"])
+def test_count_cli_reads_binary_target_lists(name, tmp_path):
+    """-f with the binary form of the same list (targets.py): same report, same log."""
+    from helpers import golden_count_output, run_count_case
+    from well_duplicates_b200 import count_cli, targets
+    case = dict([c for c in MAN["count"] if c["name"] == name][0])
+    binary = str(tmp_path / "targets.bin")
+    targets.text_to_binary(os.path.join(GOLDEN, case["targets"]), binary)
+    case["targets"] = binary
+    assert run_count_case(count_cli.main, case) == golden_count_output(case)
+
+
+def test_report_text_feeds_the_wiki_formatters_gpu(tmp_path):
+    """Lane reports of the drop-in CLI -> summarize_all_lanes (`tail`) -> the reference's wiki formatters
+    (restated in tests/wiki_formatters.py, pinned to the unmodified scripts' output in tests/golden/wiki)."""
+    import wiki_formatters as W
+    from well_duplicates_b200 import count_cli
+    from well_duplicates_b200 import workflow as wf
+    wiki = os.path.join(GOLDEN, "wiki")
+    lane_files = []
+    for lane, args in MAN["wiki"]["lanes"]:
+        out = io.StringIO()
+        with contextlib.redirect_stdout(out):
+            count_cli.main(["-f", os.path.join(GOLDEN, MAN["wiki"]["targets"]), "-r", os.path.join(GOLDEN, MAN["wiki"]["run"]), "-q"] + args)
+        path = tmp_path / ("40targets_lane%s.txt" % lane)
+        path.write_text(out.getvalue())
+        lane_files.append(str(path))
+    for tag, extra in (("all_lanes", 0), ("all_lanes_plus4", 3)):
+        text = wf.summarize_all_lanes(lane_files, levels=5, extra=extra, names=[os.path.basename(p) for p in lane_files])
+        with open(os.path.join(wiki, "40targets_%s.txt" % tag)) as fh:
+            assert text == fh.read()
+        for fn, ext in ((W.to_wiki, "wiki"), (W.to_wiki2, "wiki2.html")):
+            with open(os.path.join(wiki, "40targets_%s.%s" % (tag, ext))) as fh:
+                assert fn(text) == fh.read()
 
 
 def _load_case(eng, R, case, o):
@@ -471,7 +511,8 @@ def test_publish_counters_rows(eng, oracle):
     assert np.array_equal(buf[4], cnt.sum(axis=0))
 
 
-def test_sector_trace_equals_a_host_replay(eng, oracle):
+@pytest.mark.parametrize("chunk", [0, 8])
+def test_sector_trace_equals_a_host_replay(eng, oracle, chunk):
     """wd_count_trace_sectors (bench.py's roofline numerator): with the schedule pinned to one cycle per round,
     the sectors the fused kernel reads at position p are those of the centres (as far as the programme looks
     ahead) and of the ring wells whose first p symbols have not yet proved dist > e -- replayed with the oracle."""
@@ -487,7 +528,7 @@ def test_sector_trace_equals_a_host_replay(eng, oracle):
         eng.tile_put_bcl(0, c, td.planes[c])
     order = list(range(td.n_cycles))
     e, k, L = 2, 1, td.n_cycles
-    eng.set_tuning(step0=1, step1=1, centre_chunk=8)
+    eng.set_tuning(step0=1, step1=1, centre_chunk=chunk)
     try:
         sectors, lines = eng.trace_sectors(0, 1, order, e, False)
     finally:
@@ -508,10 +549,10 @@ def test_sector_trace_equals_a_host_replay(eng, oracle):
             for q in range(p):
                 need[q].add(int(w) >> 5)
             deepest = max(deepest, p)
-        # the centre is decoded 8 cycles at a time, as far as the deepest round looked ahead (p + k)
-        known = 0
-        while known < min(L, deepest + k):
-            known = min(L, known + 8)
+        # the centre is read as far as the deepest round looked ahead (p + k) -- exactly, or in chunks of 8 cycles
+        known = min(L, deepest + k)
+        if chunk:
+            known = min(L, (known + chunk - 1) // chunk * chunk)
         for q in range(known):
             need[q].add(int(c) >> 5)
     assert sectors[0].tolist() == [len(s) for s in need]

@@ -182,3 +182,50 @@ def test_product_never_imports_the_oracle():
                     src = fh.read()
                 assert not re.search(r"^\s*(from|import)\s+oracle\b", src, flags=re.M), f
                 assert "ref_port" not in src and "c_port" not in src and "liboracle" not in src, f
+
+
+# ---- binary target lists -----------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["ref_tests/small.list", "locs/hex_small_n40_s13.list", "locs/hex_tiny_n840_s3.list",
+                                  "locs/negative_xy_n20_s2.list"])
+def test_binary_target_list_round_trips_to_the_identical_text(name, tmp_path):
+    import io
+
+    from well_duplicates_b200 import targets as T
+    src = os.path.join(GOLDEN, name)
+    binary = str(tmp_path / "t.bin")
+    T.text_to_binary(src, binary)
+    assert T.is_binary_target_file(binary) and not T.is_binary_target_file(src)
+    text = io.StringIO()
+    T.binary_to_text(binary, text)
+    with open(src) as fh:
+        assert text.getvalue() == fh.read()
+    # the mapped list answers like the parsed one: every levels / limit combination the CLI can ask for
+    rings_on_file = T.load_targets(src).levels - 1
+    for levels in [None] + list(range(1, rings_on_file + 2)):
+        for limit in (None, 1, 5, 10 ** 6):
+            a, b = T.load_targets(src, levels=levels, limit=limit), T.load_targets(binary, levels=levels, limit=limit)
+            assert isinstance(b, T.BinaryTargets) and len(a) == len(b) and a.levels == b.levels
+            for x, y in zip(a.to_csr(), b.to_csr()):
+                assert np.array_equal(x, y)
+            assert sorted(a.get_all_indices()) == sorted(b.get_all_indices())
+            assert a.get_all_indices(0) == b.get_all_indices(0)
+            if a.levels > 1:
+                assert a.get_all_indices(1) == b.get_all_indices(1)
+                assert [t.coords for t in a] == [t.coords for t in b]
+                for r in range(a.levels):
+                    for x, y in zip(a.to_csr(r), b.to_csr(r)):
+                        assert np.array_equal(x, y)
+            with pytest.raises(IndexError):
+                b.to_csr(a.levels)
+
+
+def test_binary_target_list_rejects_what_the_text_parser_rejects(tmp_path):
+    from well_duplicates_b200 import targets as T
+    path = str(tmp_path / "dup.bin")
+    T.save_targets_binary(path, [7, 7], [0, 2, 4], [1, 2, 3, 4], 1)
+    with pytest.raises(AssertionError):
+        T.load_targets(path)                                     # duplicate centre (target.py:72)
+    with pytest.raises(ValueError):
+        T.save_targets_binary(path, [7, 8], [0, 2], [1, 2], 1)    # offsets do not match the target count
+    with pytest.raises(ValueError):
+        T.BinaryTargets(os.path.join(GOLDEN, "ref_tests", "small.list"))

@@ -113,3 +113,29 @@ def test_summary_is_what_tail_prints(tmp_path, monkeypatch, n_files, levels, ext
         names.append(name)
     want = subprocess.run(["tail", "-n", str(levels + 1 + extra)] + names, capture_output=True, text=True).stdout
     assert wf.summarize_all_lanes(names, levels, extra) == want
+
+
+# ---- the consumers of the report: GNU tail summary and the wiki formatters -------------------------
+WIKI = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "wiki")
+
+
+def _read(name):
+    with open(os.path.join(WIKI, name)) as fh:
+        return fh.read()
+
+
+@pytest.mark.parametrize("tag,extra", [("all_lanes", 0), ("all_lanes_plus4", 3)])
+def test_summary_equals_gnu_tail_of_the_reference_lane_files(tag, extra):
+    """summarize_all_lanes on the reference's own per-lane reports == what `tail -n` printed for them
+    (Snakefile.count_dups:151: levels + 1 lines; Snakefile.count_and_push:172: levels + 4)."""
+    lanes = ["40targets_lane1.txt", "40targets_lane2.txt"]
+    got = wf.summarize_all_lanes([os.path.join(WIKI, f) for f in lanes], levels=5, extra=extra, names=lanes)
+    assert got == _read("40targets_%s.txt" % tag)
+
+
+@pytest.mark.parametrize("tag", ["all_lanes", "all_lanes_plus4"])
+def test_wiki_formatter_restatements_are_pinned_to_the_reference_scripts(tag):
+    import wiki_formatters as W
+    text = _read("40targets_%s.txt" % tag)
+    assert W.to_wiki(text) == _read("40targets_%s.wiki" % tag)
+    assert W.to_wiki2(text) == _read("40targets_%s.wiki2.html" % tag)

@@ -25,10 +25,12 @@ __device__ __forceinline__ int pf_rank(const TileDesc &d, uint32_t well) {
 // s_kind[p] = WD_PLANE_* of that plane (same for every tile of a launch)
 // one base call -> raw code: 0 = no-call, otherwise base = code & 3
 // A scattered 1-byte read of a plane.  A plain load makes L2 fill the whole 128-byte line from DRAM (4 sectors
-// for 1 useful byte); the 64-byte prefetch-size qualifier is the smallest fill this part offers and halves the
-// DRAM traffic of the gather (profiles/r02_fetch_granularity_micro.txt).
+// for 1 useful byte); ld.global.nc.L2::64B is the smallest fill this part offers (profiles/
+// r02_fetch_granularity_micro.txt) and halves the DRAM bytes of the gather -- but the gather is bound by the number
+// of requests to DRAM, not by their size, and whole lines serve neighbouring targets: 64-byte fills were measured
+// 4 % SLOWER (0.398 vs 0.381 ms per 96-tile launch, profiles/r02_notes.md).  Kept as a build option.
 #ifndef WD_PLANE_LD_L2_64B
-#define WD_PLANE_LD_L2_64B 1
+#define WD_PLANE_LD_L2_64B 0
 #endif
 __device__ __forceinline__ uint32_t ld_plane_u8(const uint8_t *p) {
 #if WD_PLANE_LD_L2_64B
@@ -82,6 +84,25 @@ __device__ __forceinline__ void pseq_or_group(PSeq<W> &q, int p, uint32_t glo, u
             q.lo[i] |= (uint64_t)glo << sh;
             q.hi[i] |= (uint64_t)ghi << sh;
             q.nn[i] |= (uint64_t)gnn << sh;
+        }
+    }
+}
+
+// a 32-bit group starting at any position (may straddle a 64-bit word)
+template <int W>
+__device__ __forceinline__ void pseq_or_bits(PSeq<W> &q, int p, uint32_t glo, uint32_t ghi, uint32_t gnn) {
+    const int w = p >> 6, sh = p & 63;
+#pragma unroll
+    for (int i = 0; i < W; ++i) {
+        if (i == w) {
+            q.lo[i] |= (uint64_t)glo << sh;
+            q.hi[i] |= (uint64_t)ghi << sh;
+            q.nn[i] |= (uint64_t)gnn << sh;
+        }
+        if (i > 0 && i == w + 1 && sh > 32) {
+            q.lo[i] |= (uint64_t)glo >> (64 - sh);
+            q.hi[i] |= (uint64_t)ghi >> (64 - sh);
+            q.nn[i] |= (uint64_t)gnn >> (64 - sh);
         }
     }
 }
@@ -244,7 +265,8 @@ struct CountArgs {
     uint32_t t, n_slots;
     int levels, len, e, hamming;
     int step0, step1;                // fused kernel: cycles read per round (first, later), 1..8
-    int cchunk;                      // fused kernel: centre cycles decoded per warp-wide load (8, 16 or 32)
+    int cchunk;                      // fused kernel: 0 = the centre is read exactly as far as a round needs it; 8, 16, 32:
+                                     //   rounded up to a multiple of that (measurement sweeps)
     int n_head;                      // fused kernel: positions 0..n_head-1 are read from the tile's head planes in HBM
 };
 
@@ -406,28 +428,12 @@ __device__ __forceinline__ void trace_call(const CountArgs &a, uint32_t tile, in
     atomicOr(a.trace + ((size_t)tile * a.len + pos) * a.trace_words + (sec >> 5), 1u << (sec & 31));
 }
 
-// NMAX calls of one well at sequence positions p .. p+n-1, all loads in flight together
-template <bool ALL_BCL, int NMAX, bool TRACE>
-__device__ __forceinline__ void load_calls(const CountArgs &a, uint32_t tile, const TileDesc &d, uint32_t well, int rank,
-                                           const unsigned long long *s_off, const uint8_t *s_kind, int p, int n,
-                                           uint32_t (&raw)[NMAX]) {
-#pragma unroll
-    for (int j = 0; j < NMAX; ++j) {
-        raw[j] = 0u;
-        if (j < n) {
-            raw[j] = load_call<ALL_BCL>(d, well, rank, s_off[p + j], ALL_BCL ? 0 : s_kind[p + j]);
-            if (TRACE) trace_call<ALL_BCL>(a, tile, p + j, well, rank, ALL_BCL ? 0 : s_kind[p + j]);
-        }
-    }
-}
-
-template <int W, bool ALL_BCL, int NMAX, bool TRACE>
-__device__ __forceinline__ bool ring_round(const CountArgs &a, uint32_t tile, const TileDesc &d, uint32_t well, int rank,
-                                           const unsigned long long *s_off, const uint8_t *s_kind, const PSeq<W> &c,
-                                           int known_c, int len, int p, int n, int k, int e, bool ham_like,
-                                           PrefixDP<W> &dp, int &mism) {
-    uint32_t raw[NMAX];
-    load_calls<ALL_BCL, NMAX, TRACE>(a, tile, d, well, rank, s_off, s_kind, p, n, raw);
+// One round of a ring well: its n (<= NMAX) calls raw[0..n) at positions p .. p+n-1 are fed to the distance test;
+// false = the prefix proves dist > e.  eqtab: this warp's Eq masks of word 0 (one per symbol), for the rounds
+// inside the first 32 rows.
+template <int W, int NMAX>
+__device__ __forceinline__ bool ring_compute(const uint32_t (&raw)[8], const uint32_t *eqtab, const PSeq<W> &c, int known_c,
+                                             int len, int p, int n, int k, int e, bool ham_like, PrefixDP<W> &dp, int &mism) {
     if (ham_like) {
         uint32_t glo = 0, ghi = 0, gnn = 0;
 #pragma unroll
@@ -443,12 +449,11 @@ __device__ __forceinline__ bool ring_round(const CountArgs &a, uint32_t tile, co
         return mism <= e;
     }
     if (pdp_round_in_word0(p, n, k)) {
-        // the first round of every well: only word 0 of the programme is active (wd_seq.cuh)
-        const uint32_t alo = (uint32_t)c.lo[0], ahi = (uint32_t)c.hi[0], ann = (uint32_t)c.nn[0];
-        const uint32_t amask = len_mask32(known_c, 0);
+        // the first round of every well: only word 0 of the programme is active (wd_seq.cuh), and the Eq mask of
+        // a symbol is one shared-memory read instead of seven logic operations
 #pragma unroll
         for (int j = 0; j < NMAX; ++j)
-            if (j < n) pdp_step_word0<W>(dp, alo, ahi, ann, amask, call_symbol(raw[j]));
+            if (j < n) pdp_step_word0_eq<W>(dp, eqtab[call_symbol(raw[j])]);
         return pdp_band_min_word0<W>(dp, len, p + n, k) <= e;
     }
 #pragma unroll
@@ -457,17 +462,26 @@ __device__ __forceinline__ bool ring_round(const CountArgs &a, uint32_t tile, co
     return pdp_band_min<W>(dp, len, p + n, k) <= e;
 }
 
+// resident CTAs per SM the register allocation aims at for the common flavour (W = 1): 8 x 8 warps = every warp
+// slot of the SM at 32 registers, no spills.  The gather is bound by requests in flight: 0.368 ms per 96-tile
+// launch against 0.385 at 6 CTAs (38 registers) and 0.415 at 5 (profiles/r02_notes.md).
+#ifndef WD_FUSED_MIN_CTAS
+#define WD_FUSED_MIN_CTAS 8
+#endif
+
 template <int W, int LMAX, bool ALL_BCL, bool TRACE>
-__global__ void __launch_bounds__(CNT_WARPS * 32)
+__global__ void __launch_bounds__(CNT_WARPS * 32, W == 1 ? WD_FUSED_MIN_CTAS : 1)
 fused_count_kernel(CountArgs a) {
     __shared__ unsigned long long s_off[MAX_ORDER];
     __shared__ uint8_t s_kind[MAX_ORDER];
     __shared__ uint32_t s_cnt[1 + 5 * LMAX];
     __shared__ uint32_t s_next;
+    __shared__ uint32_t s_eq[CNT_WARPS][8];         // per warp: Eq mask of word 0 for symbols A, C, G, T, N
     for (int i = threadIdx.x; i < 1 + 5 * LMAX; i += blockDim.x) s_cnt[i] = 0;
     if (threadIdx.x == 0) s_next = 0;
     load_order(a.g_off, a.g_kind, a.len, s_off, s_kind);
     const int lane = threadIdx.x & 31;
+    uint32_t *eqtab = s_eq[threadIdx.x >> 5];
     const uint32_t tile = blockIdx.y;
     const TileDesc d = a.descs[tile];
     const int len = a.len, e = a.e;
@@ -502,7 +516,7 @@ fused_count_kernel(CountArgs a) {
         if (valid) {
             PSeq<W> c;
             pseq_clear(c);
-            int known_c = 0;
+            int known_c = 0, eq_known = -1;
             int crank = 0;
             if (!ALL_BCL && (d.flags & 1u)) crank = pf_rank(d, centre);
             for (uint32_t base = s0 + 1; base < s1; base += 32) {
@@ -523,28 +537,51 @@ fused_count_kernel(CountArgs a) {
                 while (p < len) {
                     if (!__any_sync(0xffffffffu, alive)) break;
                     const int n = min(p == 0 ? a.step0 : a.step1, len - p);
-                    // ---- centre: lane = cycle, as far as this round looks ahead ----------
-                    const int need = min(len, p + n + k);
+                    // ---- ring wells, lane = well: the round's calls, all loads in flight together ----------
+                    uint32_t raw[8];
+#pragma unroll
+                    for (int j = 0; j < 8; ++j) {
+                        raw[j] = 0u;
+                        if (alive && j < n) {
+                            raw[j] = load_call<ALL_BCL>(d, well, rank, s_off[p + j], ALL_BCL ? 0 : s_kind[p + j]);
+                            if (TRACE) trace_call<ALL_BCL>(a, tile, p + j, well, rank, ALL_BCL ? 0 : s_kind[p + j]);
+                        }
+                    }
+                    // ---- centre, lane = cycle: exactly as far as this round looks ahead (k symbols past the ring
+                    // wells; a.cchunk > 0 rounds that up), in flight together with the ring loads ------------------
+                    int need = min(len, p + n + k);
+                    if (a.cchunk > 0) need = min(len, (need + a.cchunk - 1) & ~(a.cchunk - 1));      // 8, 16 or 32
                     while (known_c < need) {
+                        const int upto = min(need, known_c + 32);
                         const int q = known_c + lane;
                         uint32_t sym = 0u;
-                        if (lane < a.cchunk && q < len) {
+                        if (q < upto) {
                             sym = call_symbol(load_call<ALL_BCL>(d, centre, crank, s_off[q], ALL_BCL ? 0 : s_kind[q]));
                             if (TRACE) trace_call<ALL_BCL>(a, tile, q, centre, crank, ALL_BCL ? 0 : s_kind[q]);
                         }
                         const uint32_t glo = __ballot_sync(0xffffffffu, sym & 1u);
                         const uint32_t ghi = __ballot_sync(0xffffffffu, sym & 2u);
                         const uint32_t gnn = __ballot_sync(0xffffffffu, sym & 4u);
-                        pseq_or_group<W>(c, known_c, glo, ghi, gnn);     // chunks never straddle a word
-                        known_c = min(len, known_c + a.cchunk);
+                        pseq_or_bits<W>(c, known_c, glo, ghi, gnn);
+                        known_c = upto;
                     }
-                    // ---- ring wells: lane = well ---------------------------------------------
+                    if (!ham_like && eq_known != known_c && pdp_round_in_word0(p, n, k)) {
+                        // Eq masks of word 0 against what is known of the centre, one per symbol
+                        __syncwarp();
+                        if (lane < 5) {
+                            const uint32_t tlo = (lane & 1) ? ~0u : 0u, thi = (lane & 2) ? ~0u : 0u, tn = (lane & 4) ? ~0u : 0u;
+                            eqtab[lane] = ~(((uint32_t)c.lo[0] ^ tlo) | ((uint32_t)c.hi[0] ^ thi) | ((uint32_t)c.nn[0] ^ tn)) &
+                                          len_mask32(known_c, 0);
+                        }
+                        __syncwarp();
+                        eq_known = known_c;
+                    }
                     if (alive) {
                         // three sizes of round are compiled (the schedules that win use 8 + 2 or 8 + 4): a
                         // smaller kernel, fewer instruction-cache misses
-                        if (n > 4) alive = ring_round<W, ALL_BCL, 8, TRACE>(a, tile, d, well, rank, s_off, s_kind, c, known_c, len, p, n, k, e, ham_like, dp, mism);
-                        else if (n > 2) alive = ring_round<W, ALL_BCL, 4, TRACE>(a, tile, d, well, rank, s_off, s_kind, c, known_c, len, p, n, k, e, ham_like, dp, mism);
-                        else alive = ring_round<W, ALL_BCL, 2, TRACE>(a, tile, d, well, rank, s_off, s_kind, c, known_c, len, p, n, k, e, ham_like, dp, mism);
+                        if (n > 4) alive = ring_compute<W, 8>(raw, eqtab, c, known_c, len, p, n, k, e, ham_like, dp, mism);
+                        else if (n > 2) alive = ring_compute<W, 4>(raw, eqtab, c, known_c, len, p, n, k, e, ham_like, dp, mism);
+                        else alive = ring_compute<W, 2>(raw, eqtab, c, known_c, len, p, n, k, e, ham_like, dp, mism);
                     }
                     p += n;
                 }

@@ -351,6 +351,19 @@ WD_HD void pdp_step_word0(PrefixDP<W> &s, uint32_t alo, uint32_t ahi, uint32_t a
     s.Mv[0] = Ph & Xv;
 }
 
+// the same step with the Eq mask of the symbol handed in (the fused kernel keeps one per symbol and centre in
+// shared memory: Eq depends on the centre and the symbol only, not on the ring well)
+template <int W>
+WD_HD void pdp_step_word0_eq(PrefixDP<W> &s, uint32_t Eq) {
+    const uint32_t pv = s.Pv[0], mv = s.Mv[0];
+    const uint32_t Xv = Eq | mv;
+    const uint32_t Xh = (((Eq & pv) + pv) ^ pv) | Eq;
+    const uint32_t Ph = ((mv | ~(Xh | pv)) << 1) | 1u;          // row 0: D[0][p+1] - D[0][p] = +1
+    const uint32_t Mh = (pv & Xh) << 1;
+    s.Pv[0] = Mh | ~(Xv | Ph);
+    s.Mv[0] = Ph & Xv;
+}
+
 // pdp_band_min for p + k <= 32 (all rows of the band in word 0)
 template <int W>
 WD_HD int pdp_band_min_word0(const PrefixDP<W> &s, int len, int p, int k) {

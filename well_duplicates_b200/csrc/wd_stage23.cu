@@ -499,7 +499,7 @@ static int count_run(wd_ctx *ctx, int first_slot, int n_tiles, const int32_t *or
     // across PCIe (wd_tile_map_host) are bound by the number of sector requests -> many short rounds
     a.step0 = over_pcie ? (n_head > 0 ? n_head : 4) : 8;       // host-mapped: the first round entirely from HBM
     a.step1 = over_pcie ? 1 : 4;
-    a.cchunk = over_pcie ? 8 : 16;
+    a.cchunk = 0;                // the centre is read exactly as far as each round looks ahead
     if (tu.step0 >= 1 && tu.step0 <= 8) a.step0 = tu.step0;
     if (tu.step1 >= 1 && tu.step1 <= 8) a.step1 = tu.step1;
     if (tu.centre_chunk == 8 || tu.centre_chunk == 16 || tu.centre_chunk == 32) a.cchunk = tu.centre_chunk;

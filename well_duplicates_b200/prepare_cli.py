@@ -29,6 +29,9 @@ def parse_args(argv=None):
     p.add_argument("-s", "--seed", dest="seed", type=int, default=None, help="seed for the random well selection")
     p.add_argument("-n", "--sample_size", dest="sample_size", type=int, default=DEF_SAMPLE_SIZE,
                    help="number of wells to sample")
+    # extension (not in the reference): the same list as arrays (targets.py), for samples too large for text
+    p.add_argument("--binary", metavar="FILE", help="write the target list to FILE in the binary format that "
+                   "count_well_duplicates.py -f also accepts, instead of printing it")
     return p.parse_args(argv)
 
 
@@ -57,8 +60,8 @@ def format_targets(centres, level_offsets, idx, levels=LEVELS):
     return "".join(x + "\n" for x in lines)
 
 
-def build_targets(xy, centres, engine=None):
-    """Rings for ``centres`` -> text of the target file.  Raises RuntimeError
+def build_targets(xy, centres, engine=None, as_arrays=False):
+    """Rings for ``centres`` -> text of the target file (or the CSR arrays).  Raises RuntimeError
     (reference :70-76) when a ring is empty."""
     eng = engine if engine is not None else default_engine()
     eng.load_locs(xy)
@@ -70,7 +73,11 @@ def build_targets(xy, centres, engine=None):
             raise
         x, y = eng.pixels()
         c = int(centres[fe[0]])
-        raise RuntimeError("Got no wells for cluster %s at (%s,%s) level %s", (c, int(x[c]), int(y[c]), fe[1]))
+        failure = RuntimeError("Got no wells for cluster %s at (%s,%s) level %s", (c, int(x[c]), int(y[c]), fe[1]))
+        failure.target_ordinal = fe[0]
+        raise failure
+    if as_arrays:
+        return offs, idx
     return format_targets(centres, offs, idx)
 
 
@@ -84,7 +91,21 @@ def main(argv=None):
     log(sample)
     if len(sample) and max(sample) >= xy.shape[0]:
         raise struct.error("unpack requires a buffer of 8 bytes")     # header promises more records than the file holds
-    sys.stdout.write(build_targets(xy, sample))
+    # get_indexes() logs the byte offset it seeks to for every centre it gets to (prepare_cluster_indexes.py:52-53)
+    def log_offsets(upto):
+        for c in sample[:upto]:
+            log(max(0, c - 20000) * 8 + 12)
+    try:
+        offs, idx = build_targets(xy, sample, as_arrays=True)
+    except RuntimeError as err:
+        log_offsets(getattr(err, "target_ordinal", -1) + 1)
+        raise
+    log_offsets(len(sample))
+    if args.binary:
+        from .targets import save_targets_binary
+        save_targets_binary(args.binary, sample, offs, idx, LEVELS)
+        return
+    sys.stdout.write(format_targets(sample, offs, idx))
 
 
 if __name__ == "__main__":
