@@ -66,7 +66,7 @@ RANDOM_LINE_REQUESTS_PER_S = 46.0e9
 def parse():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--steps", type=int, default=30)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--config", default="lane", choices=["lane", "exhaustive", "stage1", "cbcl"],
@@ -88,8 +88,8 @@ def parse():
     ap.add_argument("--sweep-steps", default="", help="wd_set_tuning sweeps timed in this process, ';'-separated: "
                                                       "'8,4' = rounds of 8 then 4 cycles, optional ',centre_chunk' and "
                                                       "'name=value' items (head_planes, head_groups, visit_order)")
-    ap.add_argument("--from-files", action="store_true", help="also time .filter/.bcl.gz files on local disk -> counters (e2e_files)")
-    ap.add_argument("--files-tiles", type=int, default=0, help="tiles per GPU for --from-files (0 = --tiles)")
+    ap.add_argument("--no-files", action="store_true", help="skip e2e_files (.filter/.bcl.gz files on local disk -> counters)")
+    ap.add_argument("--files-tiles", type=int, default=0, help="tiles per GPU for e2e_files (0 = --tiles: the whole lane)")
     ap.add_argument("--files-dir", default="/tmp/wd_bench_run")
     ap.add_argument("--cbcl-tiles", type=int, default=704, help="--config cbcl: tiles resident (a NovaSeq lane has 704)")
     ap.add_argument("--library", default="", help="A/B measurement: another build of libwelldup.so (python -m well_duplicates_b200.build --tag=...)")
@@ -116,30 +116,36 @@ class ClockSampler:
         self.proc = None
         self.lines = []
 
-    def start(self):
+    def start(self, wait_s=5.0):
+        """Starts nvidia-smi -lms 50 and waits for its first line (it can take a second to come up)."""
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "100"],
+                                          "--format=csv,noheader,nounits", "-lms", "50"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._pump, daemon=True)
             self.thread.start()
         except OSError:
             self.proc = None
+            return
+        t0 = time.time()
+        while not self.lines and time.time() - t0 < wait_s:
+            time.sleep(0.02)
 
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append((time.time(), line.strip()))
 
-    def stop(self, t0, t1):
+    def stop(self, windows):
+        """windows: [(wall t0, wall t1)] of the timed regions; only samples taken inside one of them count."""
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
-        time.sleep(0.15)
+        time.sleep(0.1)
         self.proc.terminate()
         sm, mx, reasons = [], None, set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
         for ts, line in self.lines:
             f = [x.strip() for x in line.split(",")]
-            if len(f) < 6 or not (t0 - 0.05 <= ts <= t1 + 0.15):
+            if len(f) < 6 or not any(t0 <= ts <= t1 + 0.03 for t0, t1 in windows):
                 continue
             try:
                 sm.append(float(f[0]))
@@ -150,7 +156,8 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": mx, "reasons": sorted(reasons),
-                "samples": len(sm)}
+                "samples": len(sm), "window": "samples every 50 ms inside the timed regions (value loop and e2e loops, %.2f s in all)"
+                                               % sum(t1 - t0 for t0, t1 in windows)}
 
 
 def load_peaks():
@@ -509,9 +516,10 @@ def main():
             step(False)
         counters = step(True)
         barrier()
+        # clocks are sampled from here to the end of the last timed region (value, then the e2e loops): the device-
+        # timed value loop alone is a few milliseconds, shorter than nvidia-smi's sampling period
         sampler = ClockSampler(local)
         sampler.start()
-        time.sleep(0.3)
         l0 = eng.launch_count()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t_w0 = time.time()
@@ -521,10 +529,9 @@ def main():
         eng.comm_join()                    # the last all-reduce is inside the timed region
         ev1.record(stream)
         barrier()
-        t_w1 = time.time()
+        windows = [(t_w0, time.time())]
         launches = eng.launch_count() - l0
         ms = ev0.elapsed_time(ev1)
-        clocks = sampler.stop(t_w0, t_w1)
 
         # ---- what the launch needs to read, measured (rank 0; the other ranks hold the same kind of tiles) ------
         need = needed_bytes(eng, D, n_tiles, order, centres, offs, idx, args.hamming) if (rank == 0 and args.mode != 1) else None
@@ -587,12 +594,14 @@ def main():
             zc_ok = bool(np.array_equal(zc_counters, counters))
             barrier()
             ev4, ev5 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            w0 = time.time()
             ev4.record(stream)
             for _ in range(args.e2e_steps):
                 map_tiles()
                 res = step(True)
             ev5.record(stream)
             barrier()
+            windows.append((w0, time.time()))
             zc_ms = ev4.elapsed_time(ev5) / args.e2e_steps
             d2h_per_step = int(res.size * 8)
             zc_dma_bytes = eng.last_count_h2d_bytes()
@@ -615,7 +624,9 @@ def main():
                 return r, rows
             r_log, rows_log = logged_step()
             log_ok = bool(np.array_equal(r_log, counters)) and len(rows_log) == int(my_rows[:, 2::5].sum())
+            w0 = time.time()
             zc_log_ms = timed(logged_step, args.e2e_steps)
+            windows.append((w0, time.time()))
             zc_log_pairs = int(len(rows_log))
 
             def zc_step():
@@ -637,18 +648,22 @@ def main():
             step(True)
             barrier()
             ev2, ev3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            w0 = time.time()
             ev2.record(stream)
             for _ in range(args.e2e_steps):
                 push_tiles()
                 res = step(True)
             ev3.record(stream)
             barrier()
+            windows.append((w0, time.time()))
             e2e_ms = ev2.elapsed_time(ev3) / args.e2e_steps
             d2h_per_step = int(res.size * 8)
 
+        clocks = sampler.stop(windows)
+
         # ---- from compressed files on local disk, through the staging pipeline --------------------------------
         files = None
-        if args.from_files:
+        if not args.no_files:
             from well_duplicates_b200 import staging
             from well_duplicates_b200.reader import BCLReader
             ft = args.files_tiles or n_tiles

@@ -251,3 +251,15 @@ def test_report_text_feeds_the_wiki_formatters(tmp_path, oracle_engine):
         for fn, ext in ((W.to_wiki, "wiki"), (W.to_wiki2, "wiki2.html")):
             with open(os.path.join(wiki, "40targets_%s.%s" % (tag, ext))) as fh:
                 assert fn(text) == fh.read()
+
+
+def test_empty_target_list_fails_like_the_reference(tmp_path, oracle_engine):
+    """An empty target file: the reference logs the first tile and dies with IndexError in get_seqs
+    (bcl_direct_reader.py:186, probed on the unmodified script) -- not with the library's ValueError."""
+    empty = tmp_path / "empty.list"
+    empty.write_text("")
+    err = io.StringIO()
+    with contextlib.redirect_stderr(err), pytest.raises(IndexError):
+        count_cli.main(["-f", str(empty), "-r", os.path.join(GOLDEN, "run_bcl"), "-s", "hiseq_x", "-i", "1", "-t", "1101",
+                        "-l", "5", "--cycles", "0-14"])
+    assert err.getvalue() == "Reading tile 1101 in lane 1\n"

@@ -123,6 +123,12 @@ def main(argv=None):
     cycles = parse_cycles(args)
     targets = load_targets(filename=args.coord_file, levels=args.level + 1, limit=args.sample_size)
     bcl_reader = bcl_direct_reader.BCLReader(args.run)
+    if len(targets) == 0 and tiles:
+        # an empty list: the reference opens the first tile and fails in get_seqs (bcl_direct_reader.py:186)
+        lane0 = str(lanes[0] if args.lane else 1)
+        say("Reading tile %s in lane %s" % (tiles[0], lane0))
+        bcl_reader.get_tile(lane0, tiles[0])
+        raise IndexError("list index out of range")
     eng = bcl_reader.engine
     centres, level_offsets, idx = targets.to_csr(args.level)
     eng.load_targets(centres, level_offsets, idx, args.level)

@@ -415,6 +415,30 @@ __device__ __forceinline__ uint32_t bits_at(const uint64_t *plane, int p, int n)
     return (uint32_t)v & ((1u << n) - 1u);
 }
 
+// Shared-memory reads through 32-bit shared-window addresses.  Indexing a __shared__ array through a generic
+// pointer makes the compiler rebuild the window base (S2R SR_CgaCtaId + LEA) next to every load once registers are
+// tight -- five extra instructions per plane offset in the inner loop of the fused kernel.
+__device__ __forceinline__ unsigned long long lds_u64(uint32_t addr) {
+    unsigned long long v;
+    asm("ld.shared.u64 %0, [%1];" : "=l"(v) : "r"(addr));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory");      // the Eq table is rewritten per target
+    return v;
+}
+// a value the compiler may not recompute: it has to stay in a register
+__device__ __forceinline__ uint32_t keep_in_register(uint32_t v) {
+    asm volatile("mov.u32 %0, %0;" : "+r"(v));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds_u8(uint32_t addr) {
+    uint32_t v;
+    asm("ld.shared.u8 %0, [%1];" : "=r"(v) : "r"(addr));
+    return v;
+}
+
 // measurement build: mark the 32-byte sector of the plane of position `pos` that load_call reads for this well
 template <bool ALL_BCL>
 __device__ __forceinline__ void trace_call(const CountArgs &a, uint32_t tile, int pos, uint32_t well, int rank, int kind) {
@@ -432,7 +456,7 @@ __device__ __forceinline__ void trace_call(const CountArgs &a, uint32_t tile, in
 // false = the prefix proves dist > e.  eqtab: this warp's Eq masks of word 0 (one per symbol), for the rounds
 // inside the first 32 rows.
 template <int W, int NMAX>
-__device__ __forceinline__ bool ring_compute(const uint32_t (&raw)[8], const uint32_t *eqtab, const PSeq<W> &c, int known_c,
+__device__ __forceinline__ bool ring_compute(const uint32_t (&raw)[8], uint32_t eqtab, const PSeq<W> &c, int known_c,
                                              int len, int p, int n, int k, int e, bool ham_like, PrefixDP<W> &dp, int &mism) {
     if (ham_like) {
         uint32_t glo = 0, ghi = 0, gnn = 0;
@@ -453,7 +477,7 @@ __device__ __forceinline__ bool ring_compute(const uint32_t (&raw)[8], const uin
         // a symbol is one shared-memory read instead of seven logic operations
 #pragma unroll
         for (int j = 0; j < NMAX; ++j)
-            if (j < n) pdp_step_word0_eq<W>(dp, eqtab[call_symbol(raw[j])]);
+            if (j < n) pdp_step_word0_eq<W>(dp, lds_u32(eqtab + 4u * call_symbol(raw[j])));
         return pdp_band_min_word0<W>(dp, len, p + n, k) <= e;
     }
 #pragma unroll
@@ -481,7 +505,10 @@ fused_count_kernel(CountArgs a) {
     if (threadIdx.x == 0) s_next = 0;
     load_order(a.g_off, a.g_kind, a.len, s_off, s_kind);
     const int lane = threadIdx.x & 31;
-    uint32_t *eqtab = s_eq[threadIdx.x >> 5];
+    uint32_t *eqtab_w = s_eq[threadIdx.x >> 5];
+    const uint32_t eqtab = keep_in_register((uint32_t)__cvta_generic_to_shared(eqtab_w));
+    const uint32_t off_sh = keep_in_register((uint32_t)__cvta_generic_to_shared(s_off));
+    const uint32_t kind_sh = ALL_BCL ? 0u : keep_in_register((uint32_t)__cvta_generic_to_shared(s_kind));
     const uint32_t tile = blockIdx.y;
     const TileDesc d = a.descs[tile];
     const int len = a.len, e = a.e;
@@ -543,8 +570,9 @@ fused_count_kernel(CountArgs a) {
                     for (int j = 0; j < 8; ++j) {
                         raw[j] = 0u;
                         if (alive && j < n) {
-                            raw[j] = load_call<ALL_BCL>(d, well, rank, s_off[p + j], ALL_BCL ? 0 : s_kind[p + j]);
-                            if (TRACE) trace_call<ALL_BCL>(a, tile, p + j, well, rank, ALL_BCL ? 0 : s_kind[p + j]);
+                            const int kind = ALL_BCL ? 0 : (int)lds_u8(kind_sh + p + j);
+                            raw[j] = load_call<ALL_BCL>(d, well, rank, lds_u64(off_sh + 8u * (p + j)), kind);
+                            if (TRACE) trace_call<ALL_BCL>(a, tile, p + j, well, rank, kind);
                         }
                     }
                     // ---- centre, lane = cycle: exactly as far as this round looks ahead (k symbols past the ring
@@ -556,8 +584,9 @@ fused_count_kernel(CountArgs a) {
                         const int q = known_c + lane;
                         uint32_t sym = 0u;
                         if (q < upto) {
-                            sym = call_symbol(load_call<ALL_BCL>(d, centre, crank, s_off[q], ALL_BCL ? 0 : s_kind[q]));
-                            if (TRACE) trace_call<ALL_BCL>(a, tile, q, centre, crank, ALL_BCL ? 0 : s_kind[q]);
+                            const int kind = ALL_BCL ? 0 : (int)lds_u8(kind_sh + q);
+                            sym = call_symbol(load_call<ALL_BCL>(d, centre, crank, lds_u64(off_sh + 8u * q), kind));
+                            if (TRACE) trace_call<ALL_BCL>(a, tile, q, centre, crank, kind);
                         }
                         const uint32_t glo = __ballot_sync(0xffffffffu, sym & 1u);
                         const uint32_t ghi = __ballot_sync(0xffffffffu, sym & 2u);
@@ -570,7 +599,7 @@ fused_count_kernel(CountArgs a) {
                         __syncwarp();
                         if (lane < 5) {
                             const uint32_t tlo = (lane & 1) ? ~0u : 0u, thi = (lane & 2) ? ~0u : 0u, tn = (lane & 4) ? ~0u : 0u;
-                            eqtab[lane] = ~(((uint32_t)c.lo[0] ^ tlo) | ((uint32_t)c.hi[0] ^ thi) | ((uint32_t)c.nn[0] ^ tn)) &
+                            eqtab_w[lane] = ~(((uint32_t)c.lo[0] ^ tlo) | ((uint32_t)c.hi[0] ^ thi) | ((uint32_t)c.nn[0] ^ tn)) &
                                           len_mask32(known_c, 0);
                         }
                         __syncwarp();

@@ -358,7 +358,7 @@ WD_HD void pdp_step_word0_eq(PrefixDP<W> &s, uint32_t Eq) {
     const uint32_t pv = s.Pv[0], mv = s.Mv[0];
     const uint32_t Xv = Eq | mv;
     const uint32_t Xh = (((Eq & pv) + pv) ^ pv) | Eq;
-    const uint32_t Ph = ((mv | ~(Xh | pv)) << 1) | 1u;          // row 0: D[0][p+1] - D[0][p] = +1
+    const uint32_t Ph = (mv | ~(Xh | pv)) * 2u + 1u;            // << 1, and row 0: D[0][p+1] - D[0][p] = +1 (one multiply-add)
     const uint32_t Mh = (pv & Xh) << 1;
     s.Pv[0] = Mh | ~(Xv | Ph);
     s.Mv[0] = Ph & Xv;
