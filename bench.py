@@ -520,6 +520,7 @@ def main():
         # timed value loop alone is a few milliseconds, shorter than nvidia-smi's sampling period
         sampler = ClockSampler(local)
         sampler.start()
+        barrier()                          # every rank's sampler is up: nobody waits for a late rank inside the timed loop
         l0 = eng.launch_count()
         ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         t_w0 = time.time()
@@ -605,12 +606,13 @@ def main():
             zc_ms = ev4.elapsed_time(ev5) / args.e2e_steps
             d2h_per_step = int(res.size * 8)
             zc_dma_bytes = eng.last_count_h2d_bytes()
+            zc_head, zc_dma_rate = eng.last_count_staging()
             # sectors the kernel pulls across PCIe = what it asks for beyond the head planes, measured the same way
             zc_need = None
             if rank == 0:
                 sec, _ = eng.trace_sectors(0, min(D, n_tiles), order, EDIT, args.hamming)
                 reps = np.bincount(np.arange(n_tiles) % min(D, n_tiles), minlength=min(D, n_tiles))
-                head = 2
+                head = zc_head
                 zc_need = {"pulled_sectors": int((sec[:, head:].sum(axis=1) * reps).sum()),
                            "note": "distinct 32-byte sectors of the planes behind the %d head planes that the kernel "
                                    "reads from host memory (wd_count_trace_sectors on the mapped tiles)" % head}
@@ -766,11 +768,11 @@ def main():
             line["e2e"] = {
                 "value": targets_per_step / (zc_ms / 1e3), "unit": "targets/s", "ms_per_step": zc_ms,
                 "staging": "wd_tile_map_host: planes and filters stay in pinned host memory (%.1f GB per step and GPU); "
-                           "wd_count copies the planes of the first 2 compared cycles to HBM by DMA, tile group after "
+                           "wd_count copies the planes of the first 1-2 compared cycles to HBM by DMA, tile group after "
                            "tile group, while the counting kernel reads the sectors it needs of the later planes "
                            "across PCIe" % (n_tiles * (N_CYCLES + 1) * N_WELLS / 1e9),
                 "h2d_bytes_per_step": int(zc_dma_bytes + (pulled or 0)),
-                "h2d_dma_bytes_per_step": int(zc_dma_bytes),
+                "h2d_dma_bytes_per_step": int(zc_dma_bytes), "head_planes_by_dma": zc_head, "h2d_dma_gb_per_s": zc_dma_rate,
                 "h2d_pulled_bytes_per_step": pulled,
                 "h2d_bytes_note": "per GPU. DMA bytes are counted by the library; pulled bytes = 32 B x the distinct sectors "
                                   "behind the head planes that the kernel asks for, measured in this run "

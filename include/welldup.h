@@ -85,6 +85,10 @@ WD_API int wd_set_l2_fetch_granularity(wd_ctx *ctx, int bytes, int *previous);
 /* Bytes the last wd_count / wd_count_async copied from host-mapped tiles to HBM by DMA (the planes
  * of the first compared positions, see wd_tile_map_host); 0 for staged tiles. */
 WD_API int wd_last_count_h2d_bytes(wd_ctx *ctx, uint64_t *out);
+/* Host-mapped tiles: how many leading planes the last wd_count copied by DMA (2 where copies and sector pulls
+ * overlap, 1 where the host path is shared by several GPUs and they add up -- chosen from the measured rate of
+ * an earlier count's copies unless wd_set_tuning fixes it) and that rate in GB/s (0: not measured yet). */
+WD_API int wd_last_count_staging(wd_ctx *ctx, int *head_planes, double *dma_gb_per_s);
 /* Number of kernel launches issued by this context so far (bench.py gpu_launches). */
 WD_API int wd_launch_count(wd_ctx *ctx, uint64_t *out);
 /* Knobs of wd_count for measurement sweeps (profiles/): 0 (or -1 where noted) leaves the library's choice.

@@ -61,6 +61,7 @@ SIGNATURES = {
     "wd_host_free": (C.c_int, [_p]),
     "wd_launch_count": (C.c_int, [_p, _u64p]),
     "wd_last_count_h2d_bytes": (C.c_int, [_p, _u64p]),
+    "wd_last_count_staging": (C.c_int, [_p, _i32p, C.POINTER(C.c_double)]),
     "wd_set_l2_fetch_granularity": (C.c_int, [_p, C.c_int, _i32p]),
     "wd_locs_load": (C.c_int, [_p, _p, C.c_uint32]),
     "wd_locs_pixels": (C.c_int, [_p, _p, _p]),

@@ -147,6 +147,8 @@ int wd_destroy(wd_ctx *ctx) {
         s.kind_dev.release(); s.pfcount_dev.release();
     }
     for (cudaEvent_t ev : ctx->copy_events) cudaEventDestroy(ev);
+    if (ctx->dma_ev0) cudaEventDestroy(ctx->dma_ev0);
+    if (ctx->dma_ev1) cudaEventDestroy(ctx->dma_ev1);
     if (ctx->pub_ready) cudaEventDestroy(ctx->pub_ready);
     for (cudaEvent_t ev : ctx->comm_done) if (ev) cudaEventDestroy(ev);
     if (ctx->comm_stream) cudaStreamDestroy(ctx->comm_stream);
@@ -185,6 +187,13 @@ int wd_host_free(void *p) {
 int wd_last_count_h2d_bytes(wd_ctx *ctx, uint64_t *out) {
     if (ctx == nullptr || out == nullptr) WD_FAIL(WD_E_ARG, "wd_last_count_h2d_bytes: null argument");
     *out = ctx->last_h2d_bytes;
+    return WD_OK;
+}
+
+int wd_last_count_staging(wd_ctx *ctx, int *head_planes, double *dma_gb_per_s) {
+    if (ctx == nullptr) WD_FAIL(WD_E_ARG, "wd_last_count_staging: null context");
+    if (head_planes) *head_planes = ctx->last_n_head;
+    if (dma_gb_per_s) *dma_gb_per_s = ctx->dma_gbps;
     return WD_OK;
 }
 

@@ -173,6 +173,11 @@ struct wd_ctx {
     int last_e = 0, last_hamming = 0, last_mode = 0, last_seq_len = 0;
     bool last_all_bcl = true;
     wd::DevBuf head;                  // host-mapped tiles: [tile][head plane][head stride] of the last count
+    cudaEvent_t dma_ev0 = nullptr, dma_ev1 = nullptr;   // around the head-plane copies of a count (timing)
+    bool dma_pending = false;
+    uint64_t dma_bytes_timed = 0;
+    double dma_gbps = 0.0;            // rate of the head-plane copies of an earlier count (0: not measured yet)
+    int last_n_head = 0;
     wd::DevBuf trace, trace_counts;   // wd_count_trace_sectors
     wd::DevBuf dup_codes;             // wd_dup_pairs_seqs
     wd::DevBuf excl_totals;           // wd_count_fetch: PF totals of the tiles with excluded CBCL blocks

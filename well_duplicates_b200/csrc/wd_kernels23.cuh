@@ -373,9 +373,12 @@ compare_count_kernel(CountArgs a) {
                     dup = is_duplicate<W>(c, b, a.len, a.e, a.hamming != 0);
                     if (dup && a.dup_rows != nullptr) log_dup<W>(a, tile, t, s, c, b);
                 }
+                // most passes end without a duplicate: one vote decides whether the per-level tallies are needed
+                if (__any_sync(0xffffffffu, dup)) {
 #pragma unroll
-                for (int l = 0; l < LMAX; ++l)
-                    if (l < a.levels) dups[l] += __popc(__ballot_sync(0xffffffffu, dup && lvl == l + 1));
+                    for (int l = 0; l < LMAX; ++l)
+                        if (l < a.levels) dups[l] += __popc(__ballot_sync(0xffffffffu, dup && lvl == l + 1));
+                }
             }
         }
         finish_target<LMAX>(a, tile, t, lane, valid, dups, s_cnt);
@@ -619,9 +622,12 @@ fused_count_kernel(CountArgs a) {
                 // (at p == len the band minimum is D[len][len]; Lev == Ham where Ham <= 1)
                 if (dup && a.dup_rows != nullptr)
                     log_dup_row(a, tile, t, s, ham_like ? mism : pdp_band_min<W>(dp, len, len, k));
+                // most passes end without a duplicate: one vote decides whether the per-level tallies are needed
+                if (__any_sync(0xffffffffu, dup)) {
 #pragma unroll
-                for (int l = 0; l < LMAX; ++l)
-                    if (l < a.levels) dups[l] += __popc(__ballot_sync(0xffffffffu, dup && lvl == l + 1));
+                    for (int l = 0; l < LMAX; ++l)
+                        if (l < a.levels) dups[l] += __popc(__ballot_sync(0xffffffffu, dup && lvl == l + 1));
+                }
             }
         }
         finish_target<LMAX>(a, tile, t, lane, valid, dups, s_cnt);

@@ -448,7 +448,18 @@ static int count_run(wd_ctx *ctx, int first_slot, int n_tiles, const int32_t *or
     int n_head = 0, n_groups = 1;
     size_t hstride = 0;
     if (fused && over_pcie) {
-        n_head = tu.head_planes >= 0 ? tu.head_planes : 2;          // profiles/r01_schedule_and_staging_sweeps.txt
+        // How many leading planes go by DMA: 2 where the copies run beside the sector pulls (one GPU on its host:
+        // 52 GB/s, the two overlap), 1 where the host path is shared and they add up instead (8 GPUs on one host:
+        // 61 -> 49 ms per step, profiles/r02_notes.md).  The rate of the previous count's copies tells which.
+        if (ctx->dma_pending && cudaEventQuery(ctx->dma_ev1) == cudaSuccess) {
+            float ms = 0.f;
+            if (cudaEventElapsedTime(&ms, ctx->dma_ev0, ctx->dma_ev1) == cudaSuccess && ms > 0.f)
+                ctx->dma_gbps = (double)ctx->dma_bytes_timed / ms / 1e6;
+            ctx->dma_pending = false;
+        }
+        cudaGetLastError();
+        const int adaptive = (ctx->dma_gbps > 0.0 && ctx->dma_gbps < 40.0) ? 1 : 2;
+        n_head = tu.head_planes >= 0 ? tu.head_planes : adaptive;
         n_head = std::max(0, std::min(n_head, std::min(seq_len, 8)));
         n_groups = std::max(1, std::min(tu.head_groups > 0 ? tu.head_groups : 16, n_tiles));
         hstride = ctx->slots[first_slot].stride;          // prepare_order: the same for every tile of the batch
@@ -539,6 +550,12 @@ static int count_run(wd_ctx *ctx, int first_slot, int n_tiles, const int32_t *or
         // the copies may not overtake earlier work on the compute stream that still reads the head buffer
         WD_CUDA(cudaEventRecord(ctx->copy_events[n_groups], st));
         WD_CUDA(cudaStreamWaitEvent(ctx->copy_stream, ctx->copy_events[n_groups], 0));
+        if (ctx->dma_ev0 == nullptr) {
+            WD_CUDA(cudaEventCreate(&ctx->dma_ev0));
+            WD_CUDA(cudaEventCreate(&ctx->dma_ev1));
+        }
+        const bool time_dma = !ctx->dma_pending && trace == nullptr;
+        if (time_dma) WD_CUDA(cudaEventRecord(ctx->dma_ev0, ctx->copy_stream));
         const size_t row = 1 + 2 * (size_t)L;
         for (int g = 0; g < n_groups; ++g) {
             const int t0 = (int)((long long)n_tiles * g / n_groups), t1 = (int)((long long)n_tiles * (g + 1) / n_groups);
@@ -553,6 +570,11 @@ static int count_run(wd_ctx *ctx, int first_slot, int n_tiles, const int32_t *or
             if (a.trace) ag.trace = a.trace + (size_t)t0 * seq_len * trace_words;
             launch_count_any(ctx, words, ag, t1 - t0, 0, all_bcl);
         }
+        if (time_dma) {
+            WD_CUDA(cudaEventRecord(ctx->dma_ev1, ctx->copy_stream));
+            ctx->dma_pending = true;
+            ctx->dma_bytes_timed = ctx->last_h2d_bytes;
+        }
     } else {
         launch_count_any(ctx, words, a, n_tiles, fused ? 0 : 1, all_bcl);
     }
@@ -564,6 +586,7 @@ static int count_run(wd_ctx *ctx, int first_slot, int n_tiles, const int32_t *or
     ctx->last_per_target = want_per_target != 0;
     ctx->last_all_bcl = all_bcl;
     ctx->last_seq_len = seq_len;
+    ctx->last_n_head = n_head;
     return WD_OK;
 }
 

@@ -114,6 +114,12 @@ class Engine:
         _lib.check(self._lib.wd_last_count_h2d_bytes(self._h, C.byref(n)))
         return n.value
 
+    def last_count_staging(self):
+        """-> (head planes the last count copied by DMA, GB/s measured for an earlier count's copies or 0.0)."""
+        h, r = C.c_int32(), C.c_double()
+        _lib.check(self._lib.wd_last_count_staging(self._h, C.byref(h), C.byref(r)))
+        return h.value, r.value
+
     # ---- stage 1 --------------------------------------------------------------
     def load_locs(self, xy):
         xy = _c(xy, np.float32).reshape(-1, 2)
