@@ -2,7 +2,7 @@
 # Round 2: everything the round's numbers come from, one GPU (gpurun --timeout 2400 -- bash profiles/r02_capture.sh)
 O=gpurun_out
 python -m pytest tests -m gpu -x -q > $O/r02_gpu_tests.log 2>&1; tail -3 $O/r02_gpu_tests.log
-python bench.py --from-files --files-tiles 32 > $O/r02_bench_n1.json 2> $O/r02_bench_n1.err
+python bench.py > $O/r02_bench_n1.json 2> $O/r02_bench_n1.err
 python bench.py --impl reference --steps 3 --warmup 1 > $O/r02_bench_ref.json 2> $O/r02_bench_ref.err
 for c in stage1 exhaustive cbcl; do
   python bench.py --config $c --steps 5 > $O/r02_bench_$c.json 2> $O/r02_bench_$c.err

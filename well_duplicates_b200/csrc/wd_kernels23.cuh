@@ -32,10 +32,17 @@ __device__ __forceinline__ int pf_rank(const TileDesc &d, uint32_t well) {
 #ifndef WD_PLANE_LD_L2_64B
 #define WD_PLANE_LD_L2_64B 0
 #endif
+#ifndef WD_PLANE_LD_L2_128B
+#define WD_PLANE_LD_L2_128B 0
+#endif
 __device__ __forceinline__ uint32_t ld_plane_u8(const uint8_t *p) {
 #if WD_PLANE_LD_L2_64B
     uint32_t v;
     asm("ld.global.nc.L2::64B.u8 %0, [%1];" : "=r"(v) : "l"(p));
+    return v;
+#elif WD_PLANE_LD_L2_128B
+    uint32_t v;
+    asm("ld.global.nc.L2::128B.u8 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 #else
     return __ldg(p);
@@ -320,6 +327,60 @@ __device__ __forceinline__ void log_dup_row(const CountArgs &a, uint32_t tile, u
         *reinterpret_cast<int4 *>(a.dup_rows + pos * 4) = make_int4((int)(a.tile_base + tile), (int)t, (int)slot, dist);
 }
 
+// The fused kernel's version.  Wells and Targets are the same sums for every target without a duplicate (98 % of
+// them), so they are kept in ONE register per lane across the CTA's targets -- lane l < L adds the size of ring l,
+// lane 31 counts the targets -- and reach shared memory once per warp (flush_warp_tallies); only a target with a hit
+// goes through the shared-memory counters for Dups / Hit / AccO / AccI.
+template <int LMAX>
+__device__ __forceinline__ void finish_target_fused(const CountArgs &a, uint32_t tile, uint32_t t, int lane, bool valid,
+                                                    const uint32_t *dups, uint32_t *s_cnt, uint32_t &tally) {
+    const int L = a.levels;
+    if (a.per_target != nullptr) {
+        const int row = 1 + 2 * L;
+        int32_t *pt = a.per_target + ((size_t)tile * a.t + t) * row;
+        if (lane == 0) pt[0] = valid ? 1 : 0;
+#pragma unroll
+        for (int l = 0; l < LMAX; ++l) {
+            if (l < L && lane == l) {
+                pt[1 + 2 * l] = valid ? (int32_t)dups[l] : 0;
+                pt[2 + 2 * l] = valid ? (int32_t)__ldg(a.level_len + (size_t)t * L + l) : 0;
+            }
+        }
+    }
+    if (!valid) return;
+    if (lane < L) {
+        const uint32_t ring = __ldg(a.level_len + (size_t)t * L + lane);
+        // count_well_duplicates.py:249 asserts that a ring holds wells -- for targets that get this far
+        if (ring == 0) atomicMax(a.status, ~(((unsigned long long)(a.tile_base + tile) << 32) | t));
+        tally += ring;
+    } else if (lane == 31) {
+        tally += 1u;
+    }
+    uint32_t hit_mask = 0;
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l)
+        if (l < L && dups[l]) hit_mask |= 1u << l;
+    if (hit_mask == 0) return;
+    // AccO: a hit at this level or further in; AccI: at this level or further out (count_well_duplicates.py:77-89)
+#pragma unroll
+    for (int l = 0; l < LMAX; ++l) {
+        if (l < L && lane == l) {
+            uint32_t *c = s_cnt + 1 + 5 * l;
+            if (dups[l]) {
+                atomicAdd(c + 1, dups[l]);
+                atomicAdd(c + 2, 1u);
+            }
+            if (hit_mask & ((2u << l) - 1u)) atomicAdd(c + 3, 1u);
+            if (hit_mask >> l) atomicAdd(c + 4, 1u);
+        }
+    }
+}
+
+__device__ __forceinline__ void flush_warp_tallies(int levels, int lane, uint32_t tally, uint32_t *s_cnt) {
+    if (lane < levels) atomicAdd(s_cnt + 1 + 5 * lane, tally);
+    else if (lane == 31) atomicAdd(s_cnt, tally);
+}
+
 template <int W>
 __device__ __forceinline__ void log_dup(const CountArgs &a, uint32_t tile, uint32_t t, uint32_t slot,
                                         const PSeq<W> &c, const PSeq<W> &b) {
@@ -528,6 +589,7 @@ fused_count_kernel(CountArgs a) {
     const bool read_nothing = e < 0 || (e >= len && a.dup_rows == nullptr);
     const uint32_t t_begin = blockIdx.x * FUSED_TPB;
     const uint32_t t_end = min(t_begin + FUSED_TPB, a.t);
+    uint32_t tally = 0;                                // Wells per level (lanes 0..L-1) and Targets (lane 31) of this warp
     // Targets differ a lot in cost (a failed centre costs one byte, a real
     // duplicate keeps its warp reading to the last cycle), so warps take the
     // next target when they are done instead of owning a fixed one.
@@ -569,13 +631,26 @@ fused_count_kernel(CountArgs a) {
                     const int n = min(p == 0 ? a.step0 : a.step1, len - p);
                     // ---- ring wells, lane = well: the round's calls, all loads in flight together ----------
                     uint32_t raw[8];
+                    if (n == 8) {
+                        // the first round of the resident schedule: one predicate for the eight loads
 #pragma unroll
-                    for (int j = 0; j < 8; ++j) {
-                        raw[j] = 0u;
-                        if (alive && j < n) {
-                            const int kind = ALL_BCL ? 0 : (int)lds_u8(kind_sh + p + j);
-                            raw[j] = load_call<ALL_BCL>(d, well, rank, lds_u64(off_sh + 8u * (p + j)), kind);
-                            if (TRACE) trace_call<ALL_BCL>(a, tile, p + j, well, rank, kind);
+                        for (int j = 0; j < 8; ++j) {
+                            raw[j] = 0u;
+                            if (alive) {
+                                const int kind = ALL_BCL ? 0 : (int)lds_u8(kind_sh + p + j);
+                                raw[j] = load_call<ALL_BCL>(d, well, rank, lds_u64(off_sh + 8u * (p + j)), kind);
+                                if (TRACE) trace_call<ALL_BCL>(a, tile, p + j, well, rank, kind);
+                            }
+                        }
+                    } else {
+#pragma unroll
+                        for (int j = 0; j < 8; ++j) {
+                            raw[j] = 0u;
+                            if (alive && j < n) {
+                                const int kind = ALL_BCL ? 0 : (int)lds_u8(kind_sh + p + j);
+                                raw[j] = load_call<ALL_BCL>(d, well, rank, lds_u64(off_sh + 8u * (p + j)), kind);
+                                if (TRACE) trace_call<ALL_BCL>(a, tile, p + j, well, rank, kind);
+                            }
                         }
                     }
                     // ---- centre, lane = cycle: exactly as far as this round looks ahead (k symbols past the ring
@@ -630,8 +705,9 @@ fused_count_kernel(CountArgs a) {
                 }
             }
         }
-        finish_target<LMAX>(a, tile, t, lane, valid, dups, s_cnt);
+        finish_target_fused<LMAX>(a, tile, t, lane, valid, dups, s_cnt, tally);
     }
+    flush_warp_tallies(a.levels, lane, tally, s_cnt);
     flush_counters(s_cnt, a.counters + (size_t)tile * (1 + 5 * a.levels), 1 + 5 * a.levels);
 }
 
