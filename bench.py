@@ -768,7 +768,7 @@ def main():
             line["e2e"] = {
                 "value": targets_per_step / (zc_ms / 1e3), "unit": "targets/s", "ms_per_step": zc_ms,
                 "staging": "wd_tile_map_host: planes and filters stay in pinned host memory (%.1f GB per step and GPU); "
-                           "wd_count copies the planes of the first 1-2 compared cycles to HBM by DMA, tile group after "
+                           "wd_count copies the plane of the first compared cycle (head_planes_by_dma) to HBM by DMA, tile group after "
                            "tile group, while the counting kernel reads the sectors it needs of the later planes "
                            "across PCIe" % (n_tiles * (N_CYCLES + 1) * N_WELLS / 1e9),
                 "h2d_bytes_per_step": int(zc_dma_bytes + (pulled or 0)),

@@ -85,9 +85,8 @@ WD_API int wd_set_l2_fetch_granularity(wd_ctx *ctx, int bytes, int *previous);
 /* Bytes the last wd_count / wd_count_async copied from host-mapped tiles to HBM by DMA (the planes
  * of the first compared positions, see wd_tile_map_host); 0 for staged tiles. */
 WD_API int wd_last_count_h2d_bytes(wd_ctx *ctx, uint64_t *out);
-/* Host-mapped tiles: how many leading planes the last wd_count copied by DMA (2 where copies and sector pulls
- * overlap, 1 where the host path is shared by several GPUs and they add up -- chosen from the measured rate of
- * an earlier count's copies unless wd_set_tuning fixes it) and that rate in GB/s (0: not measured yet). */
+/* Host-mapped tiles: how many leading planes the last wd_count copied by DMA (1 unless wd_set_tuning says
+ * otherwise) and the measured rate of an earlier count's copies in GB/s (0: not measured yet). */
 WD_API int wd_last_count_staging(wd_ctx *ctx, int *head_planes, double *dma_gb_per_s);
 /* Number of kernel launches issued by this context so far (bench.py gpu_launches). */
 WD_API int wd_launch_count(wd_ctx *ctx, uint64_t *out);
@@ -146,7 +145,7 @@ WD_API int wd_tile_put_cbcl(wd_ctx *ctx, int tile_slot, int plane, const uint8_t
 /* Zero-copy staging, instead of wd_tile_begin + wd_tile_put_bcl/_cbcl: the
  * tile's inflated planes stay where the host put them -- planes[p * stride_bytes]
  * in page-locked memory from wd_host_alloc().  wd_count then copies only the
- * planes of the first two compared positions to HBM (DMA, overlapped tile
+ * plane of the first compared position to HBM (DMA, overlapped tile
  * group by tile group with the kernels) and the counting kernel pulls the
  * 32-byte sectors it needs of the later planes straight across PCIe -- a few
  * per cent of a sampled tile instead of the whole 215 MB the per-cycle slurp

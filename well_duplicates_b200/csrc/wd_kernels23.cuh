@@ -28,21 +28,15 @@ __device__ __forceinline__ int pf_rank(const TileDesc &d, uint32_t well) {
 // for 1 useful byte); ld.global.nc.L2::64B is the smallest fill this part offers (profiles/
 // r02_fetch_granularity_micro.txt) and halves the DRAM bytes of the gather -- but the gather is bound by the number
 // of requests to DRAM, not by their size, and whole lines serve neighbouring targets: 64-byte fills were measured
-// 4 % SLOWER (0.398 vs 0.381 ms per 96-tile launch, profiles/r02_notes.md).  Kept as a build option.
+// 4 % SLOWER (0.398 vs 0.381 ms per 96-tile launch, profiles/r02_notes.md).  Kept as a build option.  (For planes in
+// host memory the prefetch size changes nothing: sector pulls across PCIe stay 32-byte requests, 0.35 G/s.)
 #ifndef WD_PLANE_LD_L2_64B
 #define WD_PLANE_LD_L2_64B 0
-#endif
-#ifndef WD_PLANE_LD_L2_128B
-#define WD_PLANE_LD_L2_128B 0
 #endif
 __device__ __forceinline__ uint32_t ld_plane_u8(const uint8_t *p) {
 #if WD_PLANE_LD_L2_64B
     uint32_t v;
     asm("ld.global.nc.L2::64B.u8 %0, [%1];" : "=r"(v) : "l"(p));
-    return v;
-#elif WD_PLANE_LD_L2_128B
-    uint32_t v;
-    asm("ld.global.nc.L2::128B.u8 %0, [%1];" : "=r"(v) : "l"(p));
     return v;
 #else
     return __ldg(p);

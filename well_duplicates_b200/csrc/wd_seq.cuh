@@ -367,10 +367,19 @@ WD_HD void pdp_step_word0_eq(PrefixDP<W> &s, uint32_t Eq) {
 // pdp_band_min for p + k <= 32 (all rows of the band in word 0)
 template <int W>
 WD_HD int pdp_band_min_word0(const PrefixDP<W> &s, int len, int p, int k) {
+    const uint32_t pv = s.Pv[0], mv = s.Mv[0];
+    if (k == 1 && p >= 1 && p < len) {
+        // the common band (e = 2 or 3): rows p-1, p, p+1 without a loop
+        const uint32_t below = (1u << (p - 1)) - 1u;
+        const int d0 = p + popc32(pv & below) - popc32(mv & below);                       // D[p-1][p]
+        const int d1 = d0 + (int)((pv >> (p - 1)) & 1u) - (int)((mv >> (p - 1)) & 1u);     // D[p][p]
+        const int d2 = d1 + (int)((pv >> p) & 1u) - (int)((mv >> p) & 1u);                 // D[p+1][p]
+        const int side = (d0 < d2 ? d0 : d2) + 1;
+        return d1 < side ? d1 : side;
+    }
     const int jlo = p - k > 0 ? p - k : 0;
     const int jhi = p + k < len ? p + k : len;
     const uint32_t below = jlo >= 32 ? ~0u : ((1u << jlo) - 1u);
-    const uint32_t pv = s.Pv[0], mv = s.Mv[0];
     int d = p + popc32(pv & below) - popc32(mv & below);
     int best = d + (p - jlo);
     for (int j = jlo; j < jhi; ++j) {             // row j -> j + 1 is bit j

@@ -448,9 +448,10 @@ static int count_run(wd_ctx *ctx, int first_slot, int n_tiles, const int32_t *or
     int n_head = 0, n_groups = 1;
     size_t hstride = 0;
     if (fused && over_pcie) {
-        // How many leading planes go by DMA: 2 where the copies run beside the sector pulls (one GPU on its host:
-        // 52 GB/s, the two overlap), 1 where the host path is shared and they add up instead (8 GPUs on one host:
-        // 61 -> 49 ms per step, profiles/r02_notes.md).  The rate of the previous count's copies tells which.
+        // How many leading planes go by DMA: one.  On a single GPU one, two or three planes give the same step
+        // (31.5 / 32.0 / 33.0 ms: copies and sector pulls share the PCIe read path and overlap only in part), on
+        // eight GPUs behind one host every further plane costs 12.5 ms (49 / 61 / 74 / 87 ms for 1 / 2 / 3 / 4
+        // planes) -- profiles/r02_notes.md.  The rate of the copies is measured for the record.
         if (ctx->dma_pending && cudaEventQuery(ctx->dma_ev1) == cudaSuccess) {
             float ms = 0.f;
             if (cudaEventElapsedTime(&ms, ctx->dma_ev0, ctx->dma_ev1) == cudaSuccess && ms > 0.f)
@@ -458,8 +459,7 @@ static int count_run(wd_ctx *ctx, int first_slot, int n_tiles, const int32_t *or
             ctx->dma_pending = false;
         }
         cudaGetLastError();
-        const int adaptive = (ctx->dma_gbps > 0.0 && ctx->dma_gbps < 40.0) ? 1 : 2;
-        n_head = tu.head_planes >= 0 ? tu.head_planes : adaptive;
+        n_head = tu.head_planes >= 0 ? tu.head_planes : 1;
         n_head = std::max(0, std::min(n_head, std::min(seq_len, 8)));
         n_groups = std::max(1, std::min(tu.head_groups > 0 ? tu.head_groups : 16, n_tiles));
         hstride = ctx->slots[first_slot].stride;          // prepare_order: the same for every tile of the batch
