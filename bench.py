@@ -173,7 +173,7 @@ def kernel_source_hash():
     csrc = os.path.join(ROOT, "well_duplicates_b200", "csrc")
     h = hashlib.sha256()
     for name in sorted(os.listdir(csrc)):
-        if name.endswith((".cu", ".cuh", ".cc")):
+        if name.endswith((".cu", ".cuh")):            # the .cc files are host-only (inflate, NCCL glue, page-locking)
             with open(os.path.join(csrc, name), "rb") as fh:
                 h.update(name.encode() + b"\0" + fh.read())
     return h.hexdigest()

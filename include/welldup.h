@@ -78,6 +78,10 @@ WD_API int wd_sync(wd_ctx *ctx);
 /* Pinned host memory, so that wd_tile_put_* / wd_locs_load copy by DMA without staging. */
 WD_API int wd_host_alloc(size_t bytes, void **out);
 WD_API int wd_host_free(void *p);
+/* Page-lock (and map) memory the caller already owns -- then it can be passed to wd_tile_map_host and is copied
+ * by DMA like memory from wd_host_alloc().  Unregister before freeing it. */
+WD_API int wd_host_register(void *p, size_t bytes);
+WD_API int wd_host_unregister(void *p);
 /* DRAM->L2 fill granularity hint for the current device (32, 64 or 128 bytes;
  * cudaLimitMaxL2FetchGranularity).  The scattered plane gathers use a few bytes
  * per 32-byte sector, so wd_create() asks for 32; *previous receives the old value. */

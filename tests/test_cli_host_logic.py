@@ -263,3 +263,25 @@ def test_empty_target_list_fails_like_the_reference(tmp_path, oracle_engine):
         count_cli.main(["-f", str(empty), "-r", os.path.join(GOLDEN, "run_bcl"), "-s", "hiseq_x", "-i", "1", "-t", "1101",
                         "-l", "5", "--cycles", "0-14"])
     assert err.getvalue() == "Reading tile 1101 in lane 1\n"
+
+
+def test_truncated_plane_in_mid_lane_fails_where_the_reference_would(tmp_path, oracle_engine):
+    """A .bcl.gz of the second tile is cut short.  The reference counts and logs tile 1101, logs "Reading tile 1102"
+    and dies in gzip.open().read() with EOFError (bcl_direct_reader.py:207-208).  Here the three tiles are one
+    batch whose inflate fails as a whole: lane_batches loads it again tile by tile, so tile 1101 is still counted
+    and logged before the error surfaces at tile 1102."""
+    import shutil
+    run = tmp_path / "run"
+    shutil.copytree(os.path.join(GOLDEN, "run_bcl"), run)
+    victim = run / "Data" / "Intensities" / "BaseCalls" / "L001" / "C3.1" / "s_1_1102.bcl.gz"
+    data = victim.read_bytes()
+    victim.write_bytes(data[:len(data) // 2])
+    case = [c for c in MAN["count"] if c["name"] == "lev_default"][0]
+    _, ref_err = golden_count_output(case)
+    mark = "Reading tile 1102 in lane 1\n"
+    want_err = ref_err[:ref_err.index(mark) + len(mark)]
+    out, err = io.StringIO(), io.StringIO()
+    with contextlib.redirect_stdout(out), contextlib.redirect_stderr(err), pytest.raises(EOFError):
+        count_cli.main(["-f", os.path.join(GOLDEN, case["targets"]), "-r", str(run), "-s", "hiseq_x", "-i", "1", "-t", "1101,1102,1103",
+                        "-l", "5", "--cycles", "0-14"])
+    assert out.getvalue() == "" and err.getvalue() == want_err

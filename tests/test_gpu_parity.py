@@ -381,6 +381,37 @@ def test_zero_copy_planes_equal_staged(eng, oracle):
     pinf.free()
 
 
+def test_caller_owned_memory_can_be_mapped_after_registration(eng, oracle):
+    """wd_host_register: an ordinary numpy block [tile][plane][stride] becomes usable by wd_tile_map_host
+    (zero-copy staging for callers that do not allocate through wd_host_alloc); unregistered memory is refused."""
+    R, CP = oracle
+    from well_duplicates_b200 import synth
+    from well_duplicates_b200.engine import RegisteredArray
+    X, Y, td, centres = _synthetic_tile(21, 50000, 250, 20, 300, dup_rate=0.3, shift_share=0.3)
+    eng.load_locs(synth.xy_to_locs_floats(X, Y))
+    offs, idx = eng.ring_query(centres, 5)
+    eng.load_targets(centres, offs, idx, 5)
+    stride = (td.n_wells + 255) // 256 * 256
+    block = np.zeros((2, td.n_cycles, stride), np.uint8)
+    block[:, :, :td.n_wells] = td.planes
+    filt = np.ascontiguousarray(td.filt)
+    order = list(range(td.n_cycles))
+    with pytest.raises(ValueError):
+        eng.tile_map_host(0, td.n_wells, block[0], pinned_filter=filt)          # pageable: refused
+    reg, regf = RegisteredArray(block), RegisteredArray(filt)
+    try:
+        for k in range(2):
+            eng.tile_map_host(k, td.n_wells, block[k], pinned_filter=filt)
+        pt, cnt = eng.count(0, 2, order, 2, False, mode=0)
+        wpt, wc = CP.count_tile([td.planes[c] for c in order], ["bcl"] * len(order), td.filt, centres, offs, idx, 5, 2, False)
+        for k in range(2):
+            assert np.array_equal(pt[k], wpt) and np.array_equal(cnt[k], wc)
+    finally:
+        eng.sync()
+        reg.release()
+        regf.release()
+
+
 def test_dup_pair_log_rows(eng, oracle):
     """Rows behind the stderr log: (tile, target, well, distance) in reference order."""
     R, CP = oracle
@@ -832,11 +863,18 @@ def test_flowcell_driver_single_rank(name):
     case = [c for c in MAN["count"] if c["name"] == name][0]
     with open(os.path.join(GOLDEN, "count", name + ".stdout")) as fh:
         want = fh.read()
-    argv = ["-f", os.path.join(GOLDEN, case["targets"]), "-r", os.path.join(GOLDEN, case["run"])] + case["args"] + ["-q"]
+    argv = ["-f", os.path.join(GOLDEN, case["targets"]), "-r", os.path.join(GOLDEN, case["run"])] + case["args"]
     out = io.StringIO()
     with contextlib.redirect_stdout(out):
-        flowcell.main(argv)
+        flowcell.main(argv + ["-q"])
     assert out.getvalue() == want
+    # without -q a rank logs its tiles as the reference does; on one rank that is the reference's stderr
+    with open(os.path.join(GOLDEN, "count", name + ".stderr")) as fh:
+        want_err = fh.read()
+    out, err = io.StringIO(), io.StringIO()
+    with contextlib.redirect_stdout(out), contextlib.redirect_stderr(err):
+        flowcell.main(argv)
+    assert out.getvalue() == want and err.getvalue() == want_err
 
 
 # ------------------------------------------------------- whole-run workflow --

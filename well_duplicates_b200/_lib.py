@@ -59,6 +59,8 @@ SIGNATURES = {
     "wd_sync": (C.c_int, [_p]),
     "wd_host_alloc": (C.c_int, [C.c_size_t, C.POINTER(_p)]),
     "wd_host_free": (C.c_int, [_p]),
+    "wd_host_register": (C.c_int, [_p, C.c_size_t]),
+    "wd_host_unregister": (C.c_int, [_p]),
     "wd_launch_count": (C.c_int, [_p, _u64p]),
     "wd_last_count_h2d_bytes": (C.c_int, [_p, _u64p]),
     "wd_last_count_staging": (C.c_int, [_p, _i32p, C.POINTER(C.c_double)]),

@@ -10,7 +10,8 @@ LIB = os.path.join(HERE, "libwelldup.so")
 SOURCES = ["wd_inst23_w16.cu", "wd_inst23_w8.cu", "wd_inst23_w4.cu", "wd_inst23_w2.cu", "wd_inst23_w1.cu",
            "wd_api.cu", "wd_stage1.cu", "wd_stage23.cu", "wd_exhaustive.cu",
            "wd_inflate.cc",      # host-only: gunzip of the staging pipeline
-           "wd_comm.cc"]         # host-only: NCCL communicator (libnccl is dlopen-ed on first use)
+           "wd_comm.cc",         # host-only: NCCL communicator (libnccl is dlopen-ed on first use)
+           "wd_host.cc"]         # host-only: page-locking caller memory
 HEADERS = ["wd_common.cuh", "wd_scan.cuh", "wd_seq.cuh", "wd_pack.cuh", "wd_kernels23.cuh", os.path.join("..", "..", "include", "welldup.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden", "--expt-relaxed-constexpr"]

@@ -86,6 +86,27 @@ def parse_cycles(args):
     return [(args.start, args.end)]
 
 
+def tile_log_writers(logged, centres, seq_len):
+    """``logged`` = Engine.dup_pairs(with_seqs=True) of a batch (or None) -> f(tile of the batch, say) that writes
+    that tile's duplicate pairs as the reference does (count_well_duplicates.py:258-262)."""
+    if logged is None or not len(logged[0]):
+        return lambda k, say: None
+    pairs, codes = logged
+    seqs = bcl_direct_reader.codes_to_strings(codes.reshape(-1, seq_len))
+    with_rows, at = np.unique(pairs[:, 0], return_index=True)       # rows are sorted by tile
+    first = dict(zip(with_rows.tolist(), at.tolist()))
+
+    def write(k, say):
+        i = first.get(k, len(pairs))
+        while i < len(pairs) and pairs[i, 0] == k:
+            _, t_ord, well, dist = pairs[i].tolist()
+            say("center seq at {:>07}: {}".format(int(centres[t_ord]), seqs[2 * i]))
+            say("well seq at   {:>07}: {}".format(well, seqs[2 * i + 1]))
+            say("edit distance: {}".format(dist))
+            i += 1
+    return write
+
+
 def main_exhaustive(args):
     """--exhaustive-locs: wd_count_exhaustive per tile, same report."""
     from .prepare_cli import read_locs
@@ -172,24 +193,12 @@ def main(argv=None):
         except IndexError:
             announce(names[0])         # a well beyond the tile: the reference fails on the first tile of this size
             raise
-        pairs, codes = (None, None) if args.quiet else eng.dup_pairs(with_seqs=True)
-        first = {}
-        if pairs is not None and len(pairs):
-            seqs = bcl_direct_reader.codes_to_strings(codes.reshape(-1, len(order)))
-            with_rows, at = np.unique(pairs[:, 0], return_index=True)       # rows are sorted by tile
-            first = dict(zip(with_rows.tolist(), at.tolist()))
+        tile_logs = tile_log_writers(None if args.quiet else eng.dup_pairs(with_seqs=True), centres, len(order))
         for k, name in enumerate(names):
             lane, tname = name.split("/")
             announce(name)
             say("Got %i sequences from %i contiguous cycle ranges." % (n_unique * len(cycles), len(cycles)))
-            if k in first:
-                i = first[k]
-                while i < len(pairs) and pairs[i, 0] == k:
-                    _, t_ord, well, dist = pairs[i].tolist()
-                    say("center seq at {:>07}: {}".format(int(centres[t_ord]), seqs[2 * i]))
-                    say("well seq at   {:>07}: {}".format(well, seqs[2 * i + 1]))
-                    say("edit distance: {}".format(dist))
-                    i += 1
+            tile_logs(k, say)
             lane_rows[lane][tname] = counters[k]
             todo[lane] -= 1
             if todo[lane] == 0:

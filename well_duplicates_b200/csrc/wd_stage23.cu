@@ -142,25 +142,25 @@ __global__ void publish_kernel(const unsigned long long *__restrict__ counters, 
 // ============================================================================
 // duplicate-pair log and the sector trace: small kernels behind wd_dup_pairs_seqs / wd_count_trace_sectors
 // ============================================================================
-// the two sequences of every logged pair, one byte per symbol (0..3 ACGT, 4 N): codes[row][centre, well][len]
+// the two sequences of every logged pair, one byte per symbol (0..3 ACGT, 4 N): codes[row][centre, well][len].
+// One thread per symbol: with host-mapped planes every byte is a read across PCIe, and a thread that walked a whole
+// sequence would pay those round trips one after the other (2.4 ms for the 2128 pairs of the benchmark lane).
 template <bool ALL_BCL>
 __global__ void __launch_bounds__(128)
 dup_seq_kernel(const TileDesc *__restrict__ descs, const int32_t *__restrict__ rows, unsigned long long n_rows,
                const uint32_t *__restrict__ slot_well, const uint32_t *__restrict__ tgt_off,
                const unsigned long long *__restrict__ g_off, const uint8_t *__restrict__ g_kind, int len,
                uint8_t *__restrict__ codes) {
-    __shared__ unsigned long long s_off[MAX_ORDER];
-    __shared__ uint8_t s_kind[MAX_ORDER];
-    load_order(g_off, g_kind, len, s_off, s_kind);
-    const unsigned long long i = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
-    if (i >= 2 * n_rows) return;
+    const unsigned long long j = blockIdx.x * (unsigned long long)blockDim.x + threadIdx.x;
+    if (j >= 2 * n_rows * (unsigned long long)len) return;
+    const unsigned long long i = j / (unsigned)len;           // (row, centre or well)
+    const int p = (int)(j % (unsigned)len);
     const int32_t *r = rows + (i >> 1) * 4;
     const TileDesc d = descs[r[0]];
     const uint32_t well = __ldg(slot_well + ((i & 1) ? (uint32_t)r[2] : __ldg(tgt_off + r[1])));
     int rank = 0;
     if (!ALL_BCL && (d.flags & 1u)) rank = pf_rank(d, well);
-    for (int p = 0; p < len; ++p)
-        codes[i * len + p] = (uint8_t)call_symbol(load_call<ALL_BCL>(d, well, rank, s_off[p], ALL_BCL ? 0 : s_kind[p]));
+    codes[j] = (uint8_t)call_symbol(load_call<ALL_BCL>(d, well, rank, __ldg(g_off + p), ALL_BCL ? 0 : (int)__ldg(g_kind + p)));
 }
 
 // sector bitmaps of the measurement build -> per (tile, position): distinct 32-byte sectors, distinct 128-byte lines
@@ -188,7 +188,7 @@ static void launch_dup_seq(wd_ctx *ctx, bool all_bcl, const TileDesc *descs, con
                            const uint32_t *slot_well, const uint32_t *tgt_off, int len, uint8_t *codes) {
     const unsigned long long *g_off = ctx->order_dev.as<unsigned long long>();
     const uint8_t *g_kind = ctx->order_dev.as<uint8_t>() + (size_t)MAX_ORDER * 8;
-    const unsigned blocks = (unsigned)((2 * n_rows + 127) / 128);
+    const unsigned blocks = (unsigned)((2 * n_rows * (unsigned long long)len + 127) / 128);
     if (all_bcl) dup_seq_kernel<true><<<blocks, 128, 0, ctx->stream>>>(descs, rows, n_rows, slot_well, tgt_off, g_off, g_kind, len, codes);
     else dup_seq_kernel<false><<<blocks, 128, 0, ctx->stream>>>(descs, rows, n_rows, slot_well, tgt_off, g_off, g_kind, len, codes);
     ctx->launches++;

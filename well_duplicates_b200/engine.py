@@ -70,6 +70,22 @@ class PinnedArray:
         self._fin()
 
 
+class RegisteredArray:
+    """Page-locks a numpy array the caller already has (wd_host_register), so that it can be given to
+    Engine.tile_map_host like a PinnedArray; ``release()`` (or garbage collection) unlocks it."""
+
+    def __init__(self, array):
+        if not array.flags.c_contiguous:
+            raise ValueError("only a C-contiguous array can be page-locked in place")
+        lib = _lib.load()
+        self.array = array
+        _lib.check(lib.wd_host_register(_ptr(array), array.nbytes))
+        self._fin = weakref.finalize(self, lib.wd_host_unregister, C.c_void_p(array.ctypes.data))
+
+    def release(self):
+        self._fin()
+
+
 class Engine:
     def __init__(self, device=0):
         self._lib = _lib.load()

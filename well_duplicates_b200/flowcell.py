@@ -61,12 +61,14 @@ def print_reports(stream, lanes, tiles, buf, sample_size, levels, verbose):
 
 
 def count_rank_tiles(eng, rd, stager, lanes, tiles, mine, wanted, levels, edit_distance, hamming, say=None,
-                     publish=False):
+                     publish=False, log_pairs=None):
     """Counter rows [len(mine), 1 + 5 * levels] of this rank's tiles (``mine`` = ordinals into lanes x tiles).
     Files -> page-locked planes on native threads one batch ahead of the GPU (staging.py); the planes stay in
     host memory and the fused kernel pulls the sectors it needs (wd_tile_map_host).  ``publish``: every batch's
     rows are also placed in the engine's exchange buffer on the device (K7, wd_publish_counters / _add), ready
-    for ONE all-reduce after the last batch."""
+    for ONE all-reduce after the last batch.  ``log_pairs`` = (say, centres, n_unique, n_ranges): this rank's
+    tiles are also logged as count_well_duplicates.py does without -q (:211-222, :258-262), tile by tile."""
+    from . import _lib
     from .staging import lane_batches
     rows = np.zeros((len(mine), 1 + 5 * levels), dtype=np.int64)
     names = ["%s/%s" % (lanes[int(o) // len(tiles)], tiles[int(o) % len(tiles)]) for o in mine]
@@ -78,16 +80,24 @@ def count_rank_tiles(eng, rd, stager, lanes, tiles, mine, wanted, levels, edit_d
 
     k = 0
     for got, staged in lane_batches(stager, open_tile, names, wanted):
-        for name in got:
-            lane, tile = name.split("/")
-            if say is not None:
-                say("Reading tile %s in lane %s" % (tile, lane))
         plane_of = stager.deliver(eng, staged, first_slot=0, zero_copy=True)
-        eng.count_async(0, len(got), [plane_of[c] for c in wanted], edit_distance, hamming, mode=0)
+        order = [plane_of[c] for c in wanted]
+        eng.count_async(0, len(got), order, edit_distance, hamming, mode=_lib.MODE_FUSED_LOG if log_pairs else _lib.MODE_FUSED)
         if publish:
             part = mine[k:k + len(got)]
             eng.publish_counters(part.astype(np.int32), (n_tile_rows + part // len(tiles)).astype(np.int32), n_rows, add=k > 0)
         rows[k:k + len(got)] = eng.count_fetch()[1]
+        tile_logs = None
+        if log_pairs:
+            from .count_cli import tile_log_writers
+            tile_logs = tile_log_writers(eng.dup_pairs(with_seqs=True), log_pairs[1], len(order))
+        for j, name in enumerate(got):
+            lane, tile = name.split("/")
+            if say is not None:
+                say("Reading tile %s in lane %s" % (tile, lane))
+            if tile_logs is not None:
+                log_pairs[0]("Got %i sequences from %i contiguous cycle ranges." % (log_pairs[2] * log_pairs[3], log_pairs[3]))
+                tile_logs(j, log_pairs[0])
         k += len(got)
     if publish and k == 0:
         eng.publish_counters(np.zeros(0, np.int32), np.zeros(0, np.int32), n_rows)      # a rank without tiles
@@ -119,7 +129,8 @@ def main(argv=None):
             # rendezvous only (the 128-byte NCCL id, the final barrier): the counters travel by the library's
             # own ncclAllReduce on device memory (wd_comm_init / wd_allreduce_i64)
             dist.init_process_group("gloo")
-    say = (lambda *a: None) if (args.quiet or rank != 0) else count_cli.log
+    # every rank logs its own tiles (stderr of a multi-rank run interleaves; each tile's lines stay together)
+    say = (lambda *a: None) if args.quiet else count_cli.log
 
     lanes = args.lane.split(",") if args.lane else [str(x) for x in range(1, 9)]
     tiles = count_cli.expected_tiles(args.stype, args.tile_id)
@@ -140,8 +151,9 @@ def main(argv=None):
     from .staging import Stager
     stager = Stager(threads=max(1, (os.cpu_count() or 1) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", world)))),
                     cbcl_cache=rd._cbcl_cache)
+    log_pairs = None if args.quiet else (say, centres, len(targets.get_all_indices()), len(cycles))
     count_rank_tiles(eng, rd, stager, lanes, tiles, mine, wanted, args.level, args.edit_distance, args.hamming, say,
-                     publish=True)
+                     publish=True, log_pairs=log_pairs)
     stager.close()
     # K7 has put every batch's rows into the exchange buffer on the device: one ncclAllReduce(int64, sum) over NVLink
     eng.allreduce_published()
