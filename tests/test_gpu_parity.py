@@ -412,6 +412,100 @@ def test_caller_owned_memory_can_be_mapped_after_registration(eng, oracle):
         regf.release()
 
 
+@pytest.mark.parametrize("seed", range(24))
+def test_random_configurations_vs_oracle(eng, oracle, seed):
+    """Seeded sweep over what the fused kernel's paths depend on: compared length 1..300 (1 to 8 words, centre
+    reads that straddle word boundaries), plane order with gaps and repeats, -e 0..7, Hamming or Levenshtein,
+    1..5 levels, BCL or CBCL (both block kinds), planes staged in HBM or left in page-locked host memory (head
+    planes + sector pulls), one or two tiles per launch, round sizes from wd_set_tuning.  Counters, per-target rows
+    and the duplicate-pair log (fused and two-pass) against the C oracle."""
+    R, CP = oracle
+    from well_duplicates_b200 import synth
+    from well_duplicates_b200.engine import PinnedArray
+    rng = np.random.default_rng(1000 + seed)
+    n = int(rng.integers(4000, 24000))
+    row_len = int(rng.integers(60, 200))
+    ncyc = int(rng.choice([6, 17, 33, 50, 64, 65, 90, 130]))
+    levels = int(rng.integers(1, 6))
+    e = int(rng.integers(0, 8))
+    ham = bool(rng.integers(0, 2))
+    cbcl = bool(rng.integers(0, 3) == 0)
+    mapped = bool(rng.integers(0, 2))
+    n_tiles = int(rng.integers(1, 3))
+    X, Y = synth.hex_lattice(n, row_len)
+    centres = rng.choice(n, size=int(rng.integers(20, 200)), replace=False).astype(np.uint32)
+    offs, idx = CP.rings_csr(X, Y, centres, levels)
+    eng.load_targets(centres, offs, idx, levels)
+    # compared positions: a few ranges of planes, possibly overlapping and out of order (--cycles a-b,c-d)
+    order = []
+    for _ in range(int(rng.integers(1, 4))):
+        a = int(rng.integers(0, ncyc))
+        order += list(range(a, int(rng.integers(a + 1, ncyc + 1))))
+    order = order[:300]
+    split = int(rng.integers(0, ncyc + 1))
+    tiles, pins = [], []
+    for k in range(n_tiles):
+        td = synth.make_tile(rng, n, ncyc, row_len, pf_rate=float(rng.uniform(0.3, 1.0)), dup_rate=float(rng.uniform(0.05, 0.5)),
+                             shift_share=float(rng.uniform(0, 0.6)), nocall_rate=float(rng.uniform(0, 0.05)))
+        pfmask = (td.filt & 1).astype(bool)
+        planes, kinds, nb = [], [], []
+        for c in range(ncyc):
+            if not cbcl:
+                planes.append(td.planes[c]); kinds.append("bcl"); nb.append(n)
+                continue
+            nib = synth.bcl_to_nibbles(td.planes[c])
+            if c >= split:
+                nib = nib[pfmask]
+            planes.append(synth.pack_nibbles(nib)); kinds.append("cbcl_excl" if c >= split else "cbcl"); nb.append(nib.size)
+        tiles.append((planes, kinds, nb, td.filt))
+    stride = (n + 255) // 256 * 256
+    if mapped:
+        block = PinnedArray((n_tiles, ncyc, stride))
+        block.array[:] = 0
+        fpin = PinnedArray((n_tiles, stride))
+        pins += [block, fpin]
+    for k, (planes, kinds, nb, filt) in enumerate(tiles):
+        if mapped:
+            for c in range(ncyc):
+                block.array[k, c, :planes[c].size] = planes[c]
+            fpin.array[k, :n] = filt
+            eng.tile_map_host(k, n, block.array[k], kinds=[CP.KIND[x] for x in kinds], n_block=nb, pinned_filter=fpin.array[k, :n])
+        else:
+            eng.tile_begin(k, n, ncyc)
+            eng.tile_put_filter(k, filt)
+            for c in range(ncyc):
+                if kinds[c] == "bcl":
+                    eng.tile_put_bcl(k, c, planes[c])
+                else:
+                    eng.tile_put_cbcl(k, c, planes[c], nb[c], kinds[c] == "cbcl_excl")
+    if rng.integers(0, 2):
+        eng.set_tuning(step0=int(rng.integers(1, 9)), step1=int(rng.integers(1, 9)), head_planes=int(rng.integers(0, 4)),
+                       centre_chunk=int(rng.choice([0, 8, 16, 32])), visit_order=int(rng.integers(0, 2)))
+    try:
+        want = [CP.count_tile([pl[c] for c in order], [kd[c] for c in order], filt, centres, offs, idx, levels, e, ham)
+                for pl, kd, nb, filt in tiles]
+        logs = {}
+        for mode in (0, 2, 1):
+            pt, cnt = eng.count(0, n_tiles, order, e, ham, mode=mode)
+            for k in range(n_tiles):
+                assert np.array_equal(pt[k], want[k][0]) and np.array_equal(cnt[k], want[k][1]), (seed, mode, k)
+            if mode:
+                logs[mode] = eng.dup_pairs(with_seqs=True)
+        assert np.array_equal(logs[1][0], logs[2][0]) and np.array_equal(logs[1][1], logs[2][1])
+        assert len(logs[2][0]) == int(sum(w[1][2::5].sum() for w in want))
+        if len(logs[2][0]):
+            rows, codes = logs[2]
+            k = int(rows[0, 0])
+            pl, kd, nb, filt = tiles[k]
+            wcodes, _ = CP.get_codes([pl[c] for c in order], [kd[c] for c in order], filt, rows[rows[:, 0] == k][:, 2].astype(np.int64))
+            assert np.array_equal(codes[rows[:, 0] == k][:, 1], wcodes)
+    finally:
+        eng.set_tuning()
+        eng.sync()
+        for pin in pins:
+            pin.free()
+
+
 def test_dup_pair_log_rows(eng, oracle):
     """Rows behind the stderr log: (tile, target, well, distance) in reference order."""
     R, CP = oracle
