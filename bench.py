@@ -814,7 +814,10 @@ def main():
                                     "wells_compared_per_s": wells / dt, "seconds": dt,
                                     "matches_gpu_counters": bool(ok),
                                     "sample": "%d tiles of the same lane (one per host thread), planes already gunzipped "
-                                              "in RAM; C restatement of the reference (oracle/welldup_oracle.c)" % n_cpu}
+                                              "in RAM; C restatement of the reference (oracle/welldup_oracle.c)" % n_cpu,
+                                    "python_reference_note": "the unmodified Python reference cannot travel to the GPU box; in the "
+                                                             "authoring container it needs 9.35 s per tile on one core = 267 targets/s "
+                                                             "(SURVEY section 6), 26x slower per core than this port"}
             line["counters_match_oracle"] = bool(ok)
         if not args.no_inflate and world == 1:
             line["host_inflate"] = host_inflate_sample(pins[0].array[0], os.cpu_count() or 1)
