@@ -140,11 +140,11 @@ int wd_destroy(wd_ctx *ctx) {
                       &ctx->q_flag, &ctx->descs, &ctx->order_dev, &ctx->packed, &ctx->per_target, &ctx->counters,
                       &ctx->publish, &ctx->dup_rows, &ctx->dup_count, &ctx->gs_idx, &ctx->gs_packed, &ctx->gs_codes,
                       &ctx->targets.tgt_off, &ctx->targets.slot_well, &ctx->targets.slot_level, &ctx->targets.slot_csr,
-                      &ctx->targets.level_len, &ctx->targets.visit, &ctx->head, &ctx->trace, &ctx->trace_counts, &ctx->dup_codes, &ctx->excl_totals, &ctx->x_packed, &ctx->x_counts, &ctx->x_pre, &ctx->x_ringlen, &ctx->x_flags, &ctx->x_tally, &ctx->x_work};
+                      &ctx->targets.level_len, &ctx->targets.visit, &ctx->head, &ctx->trace, &ctx->trace_counts, &ctx->dup_codes, &ctx->rank_jobs, &ctx->x_packed, &ctx->x_counts, &ctx->x_pre, &ctx->x_ringlen, &ctx->x_flags, &ctx->x_tally, &ctx->x_work};
     for (DevBuf *b : bufs) b->release();
     for (TileSlot &s : ctx->slots) {
         s.planes.release(); s.filter.release(); s.pfmask.release(); s.pfrank.release();
-        s.kind_dev.release(); s.pfcount_dev.release();
+        s.kind_dev.release();
     }
     for (cudaEvent_t ev : ctx->copy_events) cudaEventDestroy(ev);
     if (ctx->dma_ev0) cudaEventDestroy(ctx->dma_ev0);

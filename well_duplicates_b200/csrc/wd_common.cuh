@@ -74,7 +74,7 @@ struct TileSlot {
     uint32_t n = 0;
     int n_planes = 0;
     size_t stride = 0;
-    DevBuf planes, filter, pfmask, pfrank, kind_dev, pfcount_dev;
+    DevBuf planes, filter, pfmask, pfrank, kind_dev;
     uint8_t *head_ptr = nullptr;       // host-mapped: this tile's head planes inside ctx->head for the count being issued
     size_t head_stride = 0;
     const uint8_t *mapped = nullptr;   // planes left in pinned host memory (wd_tile_map_host): device view of it
@@ -180,7 +180,7 @@ struct wd_ctx {
     int last_n_head = 0;
     wd::DevBuf trace, trace_counts;   // wd_count_trace_sectors
     wd::DevBuf dup_codes;             // wd_dup_pairs_seqs
-    wd::DevBuf excl_totals;           // wd_count_fetch: PF totals of the tiles with excluded CBCL blocks
+    wd::DevBuf rank_jobs;             // K3: job descriptors of a batch of tiles
     // multi-GPU (wd_comm.cc)
     void *comm = nullptr;             // ncclComm_t
     int comm_rank = 0, comm_ranks = 1;

@@ -28,27 +28,79 @@ WD_FOR_EACH_W(WD_DECLARE_W)
 // ============================================================================
 // K3: filter bytes -> PF bit mask + block ranks
 // ============================================================================
-// one thread per 64 wells; the filter buffer is zero-padded to a multiple of 64
+// A batch of tiles in two launches (round 1: four launches and a memset per tile).  The filter bytes are read from
+// HBM; those of a host-mapped tile are brought there by DMA first (51 GB/s) -- reading them in place across PCIe
+// from the mask kernel was measured slower (331 vs 301 ms per 704-tile CBCL lane, profiles/r02_notes.md).
+struct RankJob {
+    const uint8_t *filt;     // n filter bytes, 16-byte aligned (device view)
+    uint64_t *mask;          // [nb]   PF bit per well
+    uint32_t *rank;          // [nb+1] PF wells before each block of 64; rank[nb] = the tile's PF total
+    uint32_t n, nb;
+};
+
+// one thread per 64 wells of tile blockIdx.y: mask word + its population count (kept in rank[b + 1] for the scan)
 __global__ void __launch_bounds__(256)
-filter_mask_kernel(const uint8_t *__restrict__ filt, uint32_t n_blocks, uint64_t *__restrict__ mask,
-                   uint32_t *__restrict__ cnt) {
+filter_mask_kernel(const RankJob *__restrict__ jobs) {
+    const RankJob j = jobs[blockIdx.y];
     const uint32_t b = blockIdx.x * blockDim.x + threadIdx.x;
-    if (b >= n_blocks) return;
-    const uint4 *src = reinterpret_cast<const uint4 *>(filt + (size_t)b * 64);
+    if (b >= j.nb) return;
     uint64_t m = 0;
+    if ((size_t)b * 64 + 64 <= j.n) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(j.filt + (size_t)b * 64);
 #pragma unroll
-    for (int q = 0; q < 4; ++q) {
-        const uint4 v = __ldg(src + q);
-        const uint32_t w[4] = {v.x, v.y, v.z, v.w};
+        for (int q = 0; q < 4; ++q) {
+            const uint4 v = __ldg(src + q);
+            const uint32_t w[4] = {v.x, v.y, v.z, v.w};
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-            // bit0 of each of the 4 bytes -> 4 adjacent bits
-            const uint32_t bits = (((w[k] & 0x01010101u) * 0x01020408u) >> 24) & 0xFu;
-            m |= (uint64_t)bits << (q * 16 + k * 4);
+            for (int k = 0; k < 4; ++k) {
+                // bit0 of each of the 4 bytes -> 4 adjacent bits
+                const uint32_t bits = (((w[k] & 0x01010101u) * 0x01020408u) >> 24) & 0xFu;
+                m |= (uint64_t)bits << (q * 16 + k * 4);
+            }
         }
+    } else {
+        for (uint32_t i = b * 64; i < j.n; ++i) m |= (uint64_t)(__ldg(j.filt + i) & 1u) << (i & 63);     // the tile's last block
     }
-    mask[b] = m;
-    cnt[b] = (uint32_t)__popcll(m);
+    j.mask[b] = m;
+    j.rank[b + 1] = (uint32_t)__popcll(m);
+}
+
+// one CTA per tile: rank[b] = sum of the counts in front of block b (exclusive scan in place, rank[0] = 0)
+__global__ void __launch_bounds__(1024)
+filter_rank_kernel(const RankJob *__restrict__ jobs) {
+    const RankJob j = jobs[blockIdx.x];
+    __shared__ uint32_t s_warp[32];
+    __shared__ uint32_t s_carry;
+    if (threadIdx.x == 0) { s_carry = 0; j.rank[0] = 0; }
+    __syncthreads();
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    for (uint32_t base = 0; base < j.nb; base += 1024) {
+        const uint32_t b = base + threadIdx.x;
+        const uint32_t v = b < j.nb ? j.rank[b + 1] : 0u;
+        uint32_t x = v;                                     // inclusive scan of the chunk
+#pragma unroll
+        for (int d = 1; d < 32; d <<= 1) {
+            const uint32_t y = __shfl_up_sync(0xffffffffu, x, d);
+            if (lane >= d) x += y;
+        }
+        if (lane == 31) s_warp[warp] = x;
+        __syncthreads();
+        if (warp == 0) {
+            uint32_t w = s_warp[lane];
+#pragma unroll
+            for (int d = 1; d < 32; d <<= 1) {
+                const uint32_t y = __shfl_up_sync(0xffffffffu, w, d);
+                if (lane >= d) w += y;
+            }
+            s_warp[lane] = w;
+        }
+        __syncthreads();
+        const uint32_t before = s_carry + (warp ? s_warp[warp - 1] : 0u);
+        if (b < j.nb) j.rank[b + 1] = before + x;           // inclusive at b = exclusive at b + 1
+        __syncthreads();
+        if (threadIdx.x == 1023) s_carry = before + x;
+        __syncthreads();
+    }
 }
 
 // the reference's filter_offsets list (parity hook)
@@ -60,28 +112,38 @@ filter_expand_kernel(TileDesc d, int32_t *__restrict__ out) {
 
 int filter_rank(wd_ctx *ctx, const int *slot_ids, int n) {
     cudaStream_t st = ctx->stream;
+    std::vector<RankJob> jobs;
+    uint32_t max_nb = 0;
     for (int k = 0; k < n; ++k) {
         TileSlot &s = ctx->slots[slot_ids[k]];
         if (s.rank_valid) continue;
         if (!s.filter_set) WD_FAIL(WD_E_ARG, "tile slot %d has no filter loaded", slot_ids[k]);
         const uint32_t nb = (s.n + 63) / 64;
-        if (s.mapped_filter) {
-            // K3 reads whole zero-padded 64-byte blocks: bring a mapped filter into HBM first
-            const size_t fstride = ((size_t)s.n + 255) & ~(size_t)255;
-            WD_CUDA(cudaMemcpyAsync(s.filter.p, s.mapped_filter_host, s.n, cudaMemcpyHostToDevice, st));
-            if (fstride > s.n) WD_CUDA(cudaMemsetAsync(s.filter.as<uint8_t>() + s.n, 0, fstride - s.n, st));
-        }
+        if ((size_t)nb * 8 > s.pfmask.cap || ((size_t)nb + 1) * 4 > s.pfrank.cap) WD_CUDA(cudaStreamSynchronize(st));
         WD_TRY(s.pfmask.reserve((size_t)nb * 8));
         WD_TRY(s.pfrank.reserve(((size_t)nb + 1) * 4));
-        WD_TRY(s.pfcount_dev.reserve((size_t)nb * 4));
-        WD_TRY(ctx->scan_tmp.reserve(scan_tmp_words(nb) * 4));
-        filter_mask_kernel<<<(nb + 255) / 256, 256, 0, st>>>(s.filter.as<uint8_t>(), nb, s.pfmask.as<uint64_t>(),
-                                                              s.pfcount_dev.as<uint32_t>());
-        ctx->launches++;
-        WD_CUDA(exclusive_scan_u32(s.pfcount_dev.as<uint32_t>(), s.pfrank.as<uint32_t>(), nb,
-                                   ctx->scan_tmp.as<uint32_t>(), st, &ctx->launches));
+        if (s.mapped_filter) WD_CUDA(cudaMemcpyAsync(s.filter.p, s.mapped_filter_host, s.n, cudaMemcpyHostToDevice, st));
+        RankJob j;
+        j.filt = s.filter.as<uint8_t>();
+        j.mask = s.pfmask.as<uint64_t>();
+        j.rank = s.pfrank.as<uint32_t>();
+        j.n = s.n;
+        j.nb = nb;
+        if (((uintptr_t)j.filt & 15u) != 0) WD_FAIL(WD_E_ARG, "tile slot %d: the filter bytes must be 16-byte aligned", slot_ids[k]);
+        jobs.push_back(j);
+        max_nb = std::max(max_nb, nb);
         s.rank_valid = true;
     }
+    if (jobs.empty()) return WD_OK;
+    if (jobs.size() * sizeof(RankJob) > ctx->rank_jobs.cap) WD_CUDA(cudaStreamSynchronize(st));
+    WD_TRY(ctx->rank_jobs.reserve(jobs.size() * sizeof(RankJob)));
+    WD_CUDA(cudaMemcpyAsync(ctx->rank_jobs.p, jobs.data(), jobs.size() * sizeof(RankJob), cudaMemcpyHostToDevice, st));
+    WD_CUDA(cudaStreamSynchronize(st));              // `jobs` is pageable and local
+    const RankJob *d_jobs = ctx->rank_jobs.as<RankJob>();
+    filter_mask_kernel<<<dim3((max_nb + 255) / 256, (unsigned)jobs.size()), 256, 0, st>>>(d_jobs);
+    filter_rank_kernel<<<(unsigned)jobs.size(), 1024, 0, st>>>(d_jobs);
+    ctx->launches += 2;
+    WD_CUDA(cudaGetLastError());
     return WD_OK;
 }
 
@@ -416,9 +478,11 @@ static int count_run(wd_ctx *ctx, int first_slot, int n_tiles, const int32_t *or
             WD_FAIL(WD_E_INDEX, "Requested cluster %u is out of range.  Highest on this tile is %u.", tl.max_well, s.n - 1);
     }
     if (any_excl) {
+        std::vector<int> ids(n_tiles);
+        for (int k = 0; k < n_tiles; ++k) ids[k] = first_slot + k;
+        WD_TRY(filter_rank(ctx, ids.data(), n_tiles));
         for (int k = 0; k < n_tiles; ++k) {
             const int id = first_slot + k;
-            WD_TRY(filter_rank(ctx, &id, 1));
             // every excluded block of a tile holds its PF wells (cbcl_read.py:130-131): the kernels compare the
             // count of the first with the filter's total, so the others have to agree with the first
             const TileSlot &s = ctx->slots[id];
