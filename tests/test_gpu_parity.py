@@ -516,6 +516,7 @@ def test_dup_pair_log_rows(eng, oracle):
     rows = eng.dup_pairs()
     # the fused kernel logs the same pairs with the same distances, and hands out both sequences
     eng.count(0, len(tiles), order, o["edit"], o["hamming"], mode=2)
+    eng.get_seqs(len(tiles) - 1, [3, 1], order[2:7])       # another gather in between must not disturb the log's sequences
     rows2, codes = eng.dup_pairs(with_seqs=True)
     assert np.array_equal(rows, rows2)
     log = []

@@ -701,6 +701,11 @@ int dup_seqs(wd_ctx *ctx, const std::vector<int32_t> &raw, std::vector<uint8_t> 
     if (n == 0) return WD_OK;
     cudaStream_t st = ctx->stream;
     WD_TRY(ctx->dup_codes.reserve(n * 2 * (size_t)len));
+    // the plane order and the tile descriptors of that count, in case a wd_get_seqs came in between (both are
+    // uploaded only if they differ from what the device holds)
+    bool all_bcl, any_excl;
+    WD_TRY(prepare_order(ctx, ctx->last_first_slot, ctx->last_tiles, ctx->last_order.data(), len, &all_bcl, &any_excl));
+    WD_TRY(upload_descs(ctx, ctx->last_first_slot, ctx->last_tiles));
     // the rows are still in the log buffer, in the order they were fetched in
     launch_dup_seq(ctx, ctx->last_all_bcl, ctx->descs.as<TileDesc>(), ctx->dup_rows.as<int32_t>(), n,
                    ctx->targets.slot_well.as<uint32_t>(), ctx->targets.tgt_off.as<uint32_t>(), len, ctx->dup_codes.as<uint8_t>());
