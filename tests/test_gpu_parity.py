@@ -726,6 +726,21 @@ def test_exhaustive_matches_reference_report(eng, oracle, case, tmp_path):
     assert report.format_report(case["lane"], xy.shape[0], case["tiles"], rows, o["levels"], verbose=True) == want
 
 
+@pytest.mark.parametrize("case", _exhaustive_manifest()[:2], ids=lambda c: c["name"])
+def test_every_well_through_a_binary_target_list(case, tmp_path, capsys):
+    """The reference's own route to the same report -- prepare_cluster_indexes.py -n <all wells> -s 1, then
+    count_well_duplicates.py -f <that list> -n <all wells> -- with the list written in binary form (SURVEY 8 f3:
+    the text form of a full tile is 3 GB) and counted by the sampled-mode kernels: same stdout as the reference."""
+    from well_duplicates_b200 import count_cli, prepare_cli
+    binary = str(tmp_path / "all_wells.bin")
+    prepare_cli.main(["-f", locs_path(case["locs"], tmp_path), "-n", "3072", "-s", "1", "--binary", binary])
+    capsys.readouterr()
+    count_cli.main(["-f", binary, "-n", "3072", "-r", os.path.join(GOLDEN, "run_bcl"), "-s", "hiseq_x", "-i", case["lane"],
+                    "-t", ",".join(case["tiles"]), "-q"] + case["args"])
+    with open(os.path.join(GOLDEN, "exhaustive", case["name"] + ".stdout")) as fh:
+        assert capsys.readouterr().out == fh.read()
+
+
 @pytest.mark.parametrize("case", _exhaustive_manifest(), ids=lambda c: c["name"])
 def test_exhaustive_cli_matches_reference_report(case, tmp_path):
     """count_well_duplicates.py --exhaustive-locs S_LOCS (an extension: no target file) prints what the

@@ -229,3 +229,14 @@ def test_binary_target_list_rejects_what_the_text_parser_rejects(tmp_path):
         T.save_targets_binary(path, [7, 8], [0, 2], [1, 2], 1)    # offsets do not match the target count
     with pytest.raises(ValueError):
         T.BinaryTargets(os.path.join(GOLDEN, "ref_tests", "small.list"))
+
+
+def test_nccl_is_loaded_on_demand_and_hands_out_an_id():
+    """wd_comm_unique_id needs no GPU: libnccl.so.2 is dlopen-ed on first use (csrc/wd_comm.cc); the 128 bytes are
+    what rank 0 carries to the other ranks before wd_comm_init."""
+    from well_duplicates_b200.engine import Engine
+    try:
+        a, b = Engine.comm_unique_id(), Engine.comm_unique_id()
+    except _lib.CudaError as exc:
+        pytest.skip("libnccl is not installed here: %s" % exc)
+    assert len(a) == len(b) == _lib.COMM_ID_BYTES and a != b

@@ -13,6 +13,7 @@
 #include <dlfcn.h>
 #include <nccl.h>
 
+#include <cstdio>
 #include <cstring>
 #include <mutex>
 
@@ -32,12 +33,17 @@ struct NcclApi {
 
 static NcclApi g_nccl;
 static std::once_flag g_nccl_once;
+static char g_nccl_why[256] = "not tried";          // why libnccl could not be used
 
 static const NcclApi *nccl() {
     std::call_once(g_nccl_once, [] {
         void *h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_LOCAL);
         if (h == nullptr) h = dlopen("libnccl.so", RTLD_NOW | RTLD_LOCAL);
-        if (h == nullptr) return;
+        if (h == nullptr) {
+            const char *why = dlerror();
+            snprintf(g_nccl_why, sizeof(g_nccl_why), "%s", why ? why : "dlopen failed");
+            return;
+        }
         NcclApi a;
         a.handle = h;
         a.GetUniqueId = reinterpret_cast<decltype(a.GetUniqueId)>(dlsym(h, "ncclGetUniqueId"));
@@ -46,6 +52,7 @@ static const NcclApi *nccl() {
         a.CommDestroy = reinterpret_cast<decltype(a.CommDestroy)>(dlsym(h, "ncclCommDestroy"));
         a.GetErrorString = reinterpret_cast<decltype(a.GetErrorString)>(dlsym(h, "ncclGetErrorString"));
         if (a.GetUniqueId && a.CommInitRank && a.AllReduce && a.CommDestroy && a.GetErrorString) g_nccl = a;
+        else snprintf(g_nccl_why, sizeof(g_nccl_why), "libnccl lacks one of the five entry points used");
     });
     return g_nccl.handle ? &g_nccl : nullptr;
 }
@@ -81,7 +88,7 @@ extern "C" {
 int wd_comm_unique_id(void *id128) {
     if (id128 == nullptr) WD_FAIL(WD_E_ARG, "wd_comm_unique_id: null output");
     const NcclApi *api = nccl();
-    if (api == nullptr) WD_FAIL(WD_E_CUDA, "wd_comm: libnccl.so.2 cannot be loaded (%s)", dlerror());
+    if (api == nullptr) WD_FAIL(WD_E_CUDA, "wd_comm: libnccl.so.2 cannot be used (%s)", g_nccl_why);
     static_assert(sizeof(ncclUniqueId) == WD_COMM_ID_BYTES, "ncclUniqueId is 128 bytes");
     ncclUniqueId id;
     WD_NCCL(api, api->GetUniqueId(&id));
@@ -93,7 +100,7 @@ int wd_comm_init(wd_ctx *ctx, const void *id128, int rank, int nranks) {
     if (ctx == nullptr || id128 == nullptr) WD_FAIL(WD_E_ARG, "wd_comm_init: null argument");
     if (nranks < 1 || rank < 0 || rank >= nranks) WD_FAIL(WD_E_ARG, "wd_comm_init: rank %d of %d", rank, nranks);
     const NcclApi *api = nccl();
-    if (api == nullptr) WD_FAIL(WD_E_CUDA, "wd_comm: libnccl.so.2 cannot be loaded (%s)", dlerror());
+    if (api == nullptr) WD_FAIL(WD_E_CUDA, "wd_comm: libnccl.so.2 cannot be used (%s)", g_nccl_why);
     WD_CUDA(cudaSetDevice(ctx->device));
     comm_destroy(ctx);
     ncclUniqueId id;
