@@ -19,7 +19,8 @@ HISEQ_X = "hiseq_x"
 
 
 def log(msg):
-    print(str(msg), file=sys.stderr)
+    # one write per line: the ranks of a multi-GPU run share stderr, and print() would hand text and newline over separately
+    sys.stderr.write(str(msg) + "\n")
 
 
 def parse_args(argv=None):
