@@ -672,7 +672,6 @@ def main():
             names = ["%d%d%02d" % (s, w, t) for s in (1, 2) for w in (1, 2, 3, 4) for t in range(1, 25)][:ft]
             run_dir = "%s_r%d" % (args.files_dir, rank)
             local_world = int(os.environ.get("LOCAL_WORLD_SIZE", str(world)))
-            threads = max(1, len(os.sched_getaffinity(0)) // (1 if world == 1 else 1))
             threads = max(1, (os.cpu_count() or 1) // local_world)
             t0 = time.perf_counter()
             comp_per_tile = write_lane_files(run_dir, rank + 1, names, tds[:min(D, 8)], threads)
