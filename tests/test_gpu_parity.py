@@ -435,6 +435,17 @@ def test_random_configurations_vs_oracle(eng, oracle, seed):
     X, Y = synth.hex_lattice(n, row_len)
     centres = rng.choice(n, size=int(rng.integers(20, 200)), replace=False).astype(np.uint32)
     offs, idx = CP.rings_csr(X, Y, centres, levels)
+    if seed % 3 == 0:
+        # a list with more levels than prepare_cluster_indexes writes (the library takes up to 15): every target's wells
+        # regrouped into 6..9 consecutive, non-empty levels
+        levels = int(rng.integers(6, 10))
+        offs5, idx = CP.rings_csr(X, Y, centres, 5)
+        cuts = [0]
+        for t in range(centres.size):
+            a, b = int(offs5[5 * t]), int(offs5[5 * t + 5])
+            inner = np.sort(rng.choice(np.arange(a + 1, b), size=levels - 1, replace=False))
+            cuts += inner.tolist() + [b]
+        offs = np.array(cuts, np.uint32)
     eng.load_targets(centres, offs, idx, levels)
     # compared positions: a few ranges of planes, possibly overlapping and out of order (--cycles a-b,c-d)
     order = []
