@@ -455,7 +455,13 @@ compare_count_kernel(CountArgs a) {
 //    the calls into bit-plane words), 8-32 cycles at a time and only as
 //    far ahead as the programme needs (k = e/2 symbols past the ring wells): a
 //    target without duplicates never reads its centre beyond the first chunks.
-constexpr int FUSED_TPB = 64;    // targets per CTA; its 8 warps pull them from a shared counter
+// targets per CTA; its 8 warps pull them from a shared counter.  32 = 79 CTAs per tile, 7584 per 96-tile launch = 6.4
+// waves of the 1184 resident CTAs: 0.316 ms against 0.331 with 64 targets (3.2 waves), 0.346 with 96, 0.325 with 16
+// (profiles/r02_notes.md)
+#ifndef WD_FUSED_TPB
+#define WD_FUSED_TPB 32
+#endif
+constexpr int FUSED_TPB = WD_FUSED_TPB;
 
 // raw call (0 = no-call, else base = raw & 3) -> symbol 0..3, 4 = N
 __device__ __forceinline__ uint32_t call_symbol(uint32_t raw) { return raw == 0u ? 4u : (raw & 3u); }
