@@ -260,6 +260,14 @@ def run_cbcl(args):
         l0 = eng.launch_count()
         t = _event_time(torch, stream, lambda: eng.count_async(0, T, order, EDIT, args.hamming, mode=0), args.steps)
         launches = eng.launch_count() - l0
+        # wd_set_tuning sweeps in this process (--sweep-steps, as in the lane config)
+        from bench import parse_sweep
+        sweep, schedules = {}, [x for x in getattr(args, "sweep_steps", "").split(";") if x.strip()]
+        for sch in schedules:
+            eng.set_tuning(**parse_sweep(sch))
+            eng.count_async(0, T, order, EDIT, args.hamming, mode=0)
+            sweep[sch] = {"resident_ms": 1e3 * _event_time(torch, stream, lambda: eng.count_async(0, T, order, EDIT, args.hamming, mode=0), args.steps)}
+        eng.set_tuning()
         sectors, lines = eng.trace_sectors(0, D, order, EDIT, args.hamming)
         # e2e: inflated blocks in page-locked host memory, laid out [tile][plane][stride] as the staging pipeline leaves
         # them (staging.py), mapped (wd_tile_map_host) and counted; Z distinct host tiles so that no tile slot is
@@ -285,6 +293,11 @@ def run_cbcl(args):
         ok_e2e = bool(np.array_equal(e2e_step(), cnt)) if (T % Z == 0 or Z % D == 0) else None
         t_e2e = _event_time(torch, stream, e2e_step, max(1, args.e2e_steps))
         dma_bytes = eng.last_count_h2d_bytes()
+        for sch in schedules:
+            eng.set_tuning(**parse_sweep(sch))
+            e2e_step()
+            sweep[sch]["zero_copy_ms"] = 1e3 * _event_time(torch, stream, e2e_step, max(1, args.e2e_steps))
+        eng.set_tuning()
     reps = np.bincount(np.arange(T) % D, minlength=D)
     plane_sectors = int((sectors.sum(axis=1) * reps).sum())
     need = plane_sectors * 32 + int(np.unique(centres >> 5).size) * 32 * T + int(idx.size + centres.size) * 5 + T * (1 + 5 * LEVELS) * 8
@@ -324,6 +337,7 @@ def run_cbcl(args):
         "cpu_baseline": {"value": n_cpu * 2500 / dt, "unit": "targets/s", "cores": cores, "kind": "port", "seconds": dt,
                          "sample": "%d tiles (one per host thread at a time) of the same lane, blocks already inflated in RAM; C "
                                    "restatement of the reference incl. its filter-offset table (oracle/welldup_oracle.c)" % n_cpu},
+        "sweep_steps": sweep or None,
         "counters_match_oracle": bool(ok), "counters_match_note": "all %d tile rows equal the C oracle's rows of the distinct tile they hold" % T})
     return line
 

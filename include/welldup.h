@@ -102,7 +102,9 @@ typedef struct wd_tuning {
     int32_t head_planes;   /* host-mapped tiles: compared positions whose planes are copied to HBM by DMA, 0..8; -1 default */
     int32_t head_groups;   /* ... in how many tile groups, pipelined against the counting kernels */
     int32_t visit_order;   /* 0: targets in list order; 1 or -1: in ascending order of their centre well */
-    int32_t reserved[10];
+    int32_t targets_per_cta; /* fused kernel: targets one CTA's 8 warps share, a multiple of 8 in 8..256; 0 = the library's choice */
+    int32_t ctas_per_sm;     /* fused kernel: at most this many CTAs resident per SM (1..8), by reserving shared memory; 0 = no limit */
+    int32_t reserved[8];
 } wd_tuning;
 WD_API int wd_set_tuning(wd_ctx *ctx, const wd_tuning *tuning);
 

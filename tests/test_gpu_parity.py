@@ -491,7 +491,8 @@ def test_random_configurations_vs_oracle(eng, oracle, seed):
                     eng.tile_put_cbcl(k, c, planes[c], nb[c], kinds[c] == "cbcl_excl")
     if rng.integers(0, 2):
         eng.set_tuning(step0=int(rng.integers(1, 9)), step1=int(rng.integers(1, 9)), head_planes=int(rng.integers(0, 4)),
-                       centre_chunk=int(rng.choice([0, 8, 16, 32])), visit_order=int(rng.integers(0, 2)))
+                       centre_chunk=int(rng.choice([0, 8, 16, 32])), visit_order=int(rng.integers(0, 2)),
+                       targets_per_cta=int(rng.choice([0, 8, 24, 40, 64, 256])), ctas_per_sm=int(rng.choice([0, 0, 1, 3])))
     try:
         want = [CP.count_tile([pl[c] for c in order], [kd[c] for c in order], filt, centres, offs, idx, levels, e, ham)
                 for pl, kd, nb, filt in tiles]

@@ -23,7 +23,8 @@ COMM_ID_BYTES = 128
 class Tuning(C.Structure):
     """struct wd_tuning (include/welldup.h)."""
     _fields_ = [("step0", C.c_int32), ("step1", C.c_int32), ("centre_chunk", C.c_int32), ("head_planes", C.c_int32),
-                ("head_groups", C.c_int32), ("visit_order", C.c_int32), ("reserved", C.c_int32 * 10)]
+                ("head_groups", C.c_int32), ("visit_order", C.c_int32), ("targets_per_cta", C.c_int32),
+                ("ctas_per_sm", C.c_int32), ("reserved", C.c_int32 * 8)]
 
 
 class CudaError(RuntimeError):

@@ -125,6 +125,11 @@ int wd_set_tuning(wd_ctx *ctx, const wd_tuning *t) {
         tu.head_planes = t->head_planes;
         tu.head_groups = t->head_groups;
         tu.visit_order = t->visit_order;
+        if (t->targets_per_cta != 0 && (t->targets_per_cta < 8 || t->targets_per_cta > 256 || t->targets_per_cta % 8 != 0))
+            WD_FAIL(WD_E_ARG, "wd_set_tuning: targets_per_cta is a multiple of 8 in 8..256 (0 = default)");
+        if (t->ctas_per_sm < 0 || t->ctas_per_sm > 8) WD_FAIL(WD_E_ARG, "wd_set_tuning: ctas_per_sm is 1..8 (0 = no limit)");
+        tu.targets_per_cta = t->targets_per_cta;
+        tu.ctas_per_sm = t->ctas_per_sm;
     }
     ctx->tuning = tu;
     return WD_OK;

@@ -121,6 +121,8 @@ struct Tuning {
     int head_planes = -1;          // host-mapped tiles: compared positions whose planes go to HBM by DMA, 0..8
     int head_groups = 0;           // ... in how many tile groups, pipelined against the counting kernels
     int visit_order = -1;          // 0: targets in list order, 1 / -1: in ascending order of their centre well
+    int targets_per_cta = 0;       // fused kernel: targets per CTA (8..256), 0 = chosen per launch
+    int ctas_per_sm = 0;           // fused kernel: resident CTAs per SM capped by reserving shared memory, 0 = no cap
 };
 
 }  // namespace wd

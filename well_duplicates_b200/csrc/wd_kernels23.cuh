@@ -269,6 +269,9 @@ struct CountArgs {
     int cchunk;                      // fused kernel: 0 = the centre is read exactly as far as a round needs it; 8, 16, 32:
                                      //   rounded up to a multiple of that (measurement sweeps)
     int n_head;                      // fused kernel: positions 0..n_head-1 are read from the tile's head planes in HBM
+    int tpb;                         // fused kernel: targets per CTA (grid.x = ceil(t / tpb))
+    int pad_smem;                    // fused kernel (host side only): bytes of dynamic shared memory the launch reserves to
+                                     //   cap the CTAs resident per SM
 };
 
 // Per-warp tallies -> per_target row and the CTA's shared counters.
@@ -455,13 +458,8 @@ compare_count_kernel(CountArgs a) {
 //    the calls into bit-plane words), 8-32 cycles at a time and only as
 //    far ahead as the programme needs (k = e/2 symbols past the ring wells): a
 //    target without duplicates never reads its centre beyond the first chunks.
-// targets per CTA; its 8 warps pull them from a shared counter.  32 = 79 CTAs per tile, 7584 per 96-tile launch = 6.4
-// waves of the 1184 resident CTAs: 0.316 ms against 0.331 with 64 targets (3.2 waves), 0.346 with 96, 0.325 with 16
-// (profiles/r02_notes.md)
-#ifndef WD_FUSED_TPB
-#define WD_FUSED_TPB 32
-#endif
-constexpr int FUSED_TPB = WD_FUSED_TPB;
+// Targets per CTA (CountArgs::tpb): its 8 warps pull them from a shared counter.  count_run chooses the number per
+// launch (wd_stage23.cu, measurements in profiles/r02_notes.md); wd_set_tuning overrides it.
 
 // raw call (0 = no-call, else base = raw & 3) -> symbol 0..3, 4 = N
 __device__ __forceinline__ uint32_t call_symbol(uint32_t raw) { return raw == 0u ? 4u : (raw & 3u); }
@@ -587,8 +585,8 @@ fused_count_kernel(CountArgs a) {
     const int k = ham_like ? 0 : (e >> 1);
     // no pair / every pair is a duplicate -- but the log wants the distance of every duplicate
     const bool read_nothing = e < 0 || (e >= len && a.dup_rows == nullptr);
-    const uint32_t t_begin = blockIdx.x * FUSED_TPB;
-    const uint32_t t_end = min(t_begin + FUSED_TPB, a.t);
+    const uint32_t t_begin = blockIdx.x * (uint32_t)a.tpb;
+    const uint32_t t_end = min(t_begin + (uint32_t)a.tpb, a.t);
     uint32_t tally = 0;                                // Wells per level (lanes 0..L-1) and Targets (lane 31) of this warp
     // Targets differ a lot in cost (a failed centre costs one byte, a real
     // duplicate keeps its warp reading to the last cycle), so warps take the
@@ -743,10 +741,17 @@ void launch_unpack_w(wd_ctx *ctx, const uint64_t *packed, uint32_t n_idx, int le
     ctx->launches++;
 }
 
+// a launch may reserve most of the SM's shared memory (CountArgs::pad_smem, a measurement knob: asked per launch)
+template <class K>
+void allow_dynamic_smem(K kernel) {
+    cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 200 * 1024);
+}
+
 template <int W, int LMAX>
 void launch_count(wd_ctx *ctx, const CountArgs &a, int n_tiles, int mode, bool all_bcl) {
     dim3 grid((a.t + CNT_WARPS - 1) / CNT_WARPS, n_tiles);
-    dim3 fgrid((a.t + FUSED_TPB - 1) / FUSED_TPB, n_tiles);
+    dim3 fgrid((a.t + a.tpb - 1) / a.tpb, n_tiles);
+    const size_t pad = (size_t)std::max(0, a.pad_smem);
     if (mode == 1) {
         compare_count_kernel<W, LMAX><<<grid, CNT_WARPS * 32, 0, ctx->stream>>>(a);
     } else if (a.trace != nullptr) {
@@ -756,9 +761,11 @@ void launch_count(wd_ctx *ctx, const CountArgs &a, int n_tiles, int mode, bool a
             else fused_count_kernel<1, 5, false, true><<<fgrid, CNT_WARPS * 32, 0, ctx->stream>>>(a);
         }
     } else if (all_bcl) {
-        fused_count_kernel<W, LMAX, true, false><<<fgrid, CNT_WARPS * 32, 0, ctx->stream>>>(a);
+        if (pad > 48 * 1024) allow_dynamic_smem(fused_count_kernel<W, LMAX, true, false>);
+        fused_count_kernel<W, LMAX, true, false><<<fgrid, CNT_WARPS * 32, pad, ctx->stream>>>(a);
     } else {
-        fused_count_kernel<W, LMAX, false, false><<<fgrid, CNT_WARPS * 32, 0, ctx->stream>>>(a);
+        if (pad > 48 * 1024) allow_dynamic_smem(fused_count_kernel<W, LMAX, false, false>);
+        fused_count_kernel<W, LMAX, false, false><<<fgrid, CNT_WARPS * 32, pad, ctx->stream>>>(a);
     }
     ctx->launches++;
 }

@@ -579,6 +579,22 @@ static int count_run(wd_ctx *ctx, int first_slot, int n_tiles, const int32_t *or
     if (tu.step1 >= 1 && tu.step1 <= 8) a.step1 = tu.step1;
     if (tu.centre_chunk == 8 || tu.centre_chunk == 16 || tu.centre_chunk == 32) a.cchunk = tu.centre_chunk;
     a.n_head = n_head;
+    // Targets per CTA.  A CTA's warps share its targets and wait for the slowest at the end; CTAs come in waves of
+    // sm_count x 8.  Planes in HBM (sweeps of 16..128 in profiles/r02_notes.md section 2): a 96-tile lane is fastest
+    // with 32 (6.4 waves; 64 = 3.2 waves is 4 % slower), the 704-tile CBCL lane with 128 (10 % faster than 32): as many
+    // as leave six waves, between 32 and 128.  Host-mapped tiles: the sector pulls across PCIe are bound by the
+    // requests in flight, and fewer, longer-lived CTAs are faster (BCL lane: 31.0 ms with 256 or 128, 32.2 with 64, 34.7 with 32;
+    // 704-tile CBCL lane: 251 ms with 256, 286 with 128, 289 with 64)
+    {
+        const size_t resident = (size_t)ctx->sm_count * 8;
+        const size_t per_launch = (size_t)tl.t * (size_t)std::max(1, n_tiles / std::max(1, n_groups));
+        size_t tpb = over_pcie ? 256 : std::min<size_t>(128, per_launch / (6 * resident));
+        tpb = std::max<size_t>(32, tpb / 8 * 8);
+        a.tpb = (int)tpb;
+    }
+    if (tu.targets_per_cta >= 8) a.tpb = tu.targets_per_cta;
+    // wd_set_tuning only: cap the CTAs resident per SM by reserving shared memory (227 KB per SM, ~11 KB per CTA static)
+    a.pad_smem = tu.ctas_per_sm > 0 ? std::min(200 * 1024, std::max(0, (227 * 1024) / tu.ctas_per_sm - 12 * 1024) / 1024 * 1024) : 0;
 
     if (!fused) {
         WD_TRY(ctx->packed.reserve((size_t)n_tiles * tl.n_slots * words * PACK_STRIDE * 8));

@@ -114,10 +114,12 @@ class Engine:
         _lib.check(self._lib.wd_set_l2_fetch_granularity(self._h, int(nbytes), C.byref(prev)))
         return prev.value
 
-    def set_tuning(self, step0=0, step1=0, centre_chunk=0, head_planes=-1, head_groups=0, visit_order=-1):
+    def set_tuning(self, step0=0, step1=0, centre_chunk=0, head_planes=-1, head_groups=0, visit_order=-1, targets_per_cta=0,
+                   ctas_per_sm=0):
         """Measurement knobs of wd_count (struct wd_tuning); no arguments = the library's defaults."""
         t = _lib.Tuning(step0=int(step0), step1=int(step1), centre_chunk=int(centre_chunk), head_planes=int(head_planes),
-                        head_groups=int(head_groups), visit_order=int(visit_order))
+                        head_groups=int(head_groups), visit_order=int(visit_order),
+                        targets_per_cta=int(targets_per_cta), ctas_per_sm=int(ctas_per_sm))
         _lib.check(self._lib.wd_set_tuning(self._h, C.byref(t)))
 
     def launch_count(self):
