@@ -45,6 +45,8 @@ from concurrent.futures import ThreadPoolExecutor
 
 import numpy as np
 
+from bench_configs import parse_sweep
+
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
 
@@ -345,21 +347,6 @@ def workload_config(args, per_gpu_tiles):
             "l2": "inputs (%.1f GB of planes per GPU) are far larger than L2; no flush needed" % (
                 per_gpu_tiles * N_WELLS * N_CYCLES / 1e9),
             "parallelism": "tiles sharded ordinal % n_gpus; one int64 all-reduce of the counter rows per step"}
-
-
-def parse_sweep(item):
-    """'8,4[,16] head_planes=3 ...' -> keyword arguments of Engine.set_tuning."""
-    kw = {}
-    for part in item.split():
-        if "=" in part:
-            k, v = part.split("=", 1)
-            kw[k] = int(v)
-        else:
-            f = [int(x) for x in part.split(",")]
-            kw["step0"], kw["step1"] = f[0], f[1]
-            if len(f) > 2:
-                kw["centre_chunk"] = f[2]
-    return kw
 
 
 def write_lane_files(run_dir, lane, names, distinct_tiles, threads):

@@ -32,6 +32,21 @@ def _peak():
     return load_peaks()
 
 
+def parse_sweep(item):
+    """'8,4[,16] head_planes=3 ...' -> keyword arguments of Engine.set_tuning."""
+    kw = {}
+    for part in item.split():
+        if "=" in part:
+            k, v = part.split("=", 1)
+            kw[k] = int(v)
+        else:
+            f = [int(x) for x in part.split(",")]
+            kw["step0"], kw["step1"] = f[0], f[1]
+            if len(f) > 2:
+                kw["centre_chunk"] = f[2]
+    return kw
+
+
 def _event_time(torch, stream, fn, reps):
     torch.cuda.synchronize()
     a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -261,7 +276,6 @@ def run_cbcl(args):
         t = _event_time(torch, stream, lambda: eng.count_async(0, T, order, EDIT, args.hamming, mode=0), args.steps)
         launches = eng.launch_count() - l0
         # wd_set_tuning sweeps in this process (--sweep-steps, as in the lane config)
-        from bench import parse_sweep
         sweep, schedules = {}, [x for x in getattr(args, "sweep_steps", "").split(";") if x.strip()]
         for sch in schedules:
             eng.set_tuning(**parse_sweep(sch))

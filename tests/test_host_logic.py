@@ -240,3 +240,26 @@ def test_nccl_is_loaded_on_demand_and_hands_out_an_id():
     except _lib.CudaError as exc:
         pytest.skip("libnccl is not installed here: %s" % exc)
     assert len(a) == len(b) == _lib.COMM_ID_BYTES and a != b
+
+
+def test_tuning_struct_matches_the_header_and_bench_sweep_items_map_onto_it():
+    """wd_tuning (include/welldup.h) is 16 int32 whatever fields are named; every field the header declares is a
+    field of the ctypes mirror and a keyword of Engine.set_tuning, and a bench.py --sweep-steps item parses to them."""
+    import ctypes
+    import inspect
+    import re
+    from bench_configs import parse_sweep
+    from well_duplicates_b200 import _lib
+    from well_duplicates_b200.engine import Engine
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    header = open(os.path.join(root, "include", "welldup.h")).read()
+    body = header[header.index("typedef struct wd_tuning"):header.index("} wd_tuning;")]
+    declared = [re.fullmatch(r"(\w+)(?:\[(\d+)\])?", item.strip()).groups()
+                for decl in re.findall(r"int32_t\s+([^;]+);", body) for item in decl.split(",")]
+    names = [n for n, dim in declared if not dim]
+    assert sum(int(dim or 1) for _, dim in declared) == 16 and ctypes.sizeof(_lib.Tuning) == 64
+    assert [f[0] for f in _lib.Tuning._fields_ if f[0] != "reserved"] == names
+    assert set(names) <= set(inspect.signature(Engine.set_tuning).parameters)
+    kw = parse_sweep("8,4,16 head_planes=3 targets_per_cta=64 ctas_per_sm=2")
+    assert kw == {"step0": 8, "step1": 4, "centre_chunk": 16, "head_planes": 3, "targets_per_cta": 64, "ctas_per_sm": 2}
+    assert set(kw) <= set(names)
